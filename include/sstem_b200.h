@@ -1,0 +1,150 @@
+/*
+ * sstem_b200.h -- C ABI of the B200-native (sm_100a) hot path of
+ * sydeng99/ssTEM-restoration: the 51-tap adaptive separable local convolution
+ * (forward, grad w.r.t. vertical / horizontal taps, grad w.r.t. input) and the
+ * flow-driven bilinear backward warps.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / THC types.
+ * Each entry point names the reference interface it replaces (paths relative to
+ * the reference checkout).  INTEGRATION.md shows the binding a maintainer of the
+ * reference would add (ctypes, as the reference bound its THC library via cffi in
+ * libs/sepconv/_ext/cunnex/__init__.py:2-15).
+ *
+ * Conventions
+ *   - every pointer is DEVICE memory on one GPU; fp32 unless stated; tensors are
+ *     contiguous NCHW exactly as the reference asserts
+ *     (libs/sepconv/SeparableConvolution.py:33-35);
+ *   - the caller allocates every output; the callee overwrites all of it (no
+ *     zero-fill needed, unlike SeparableConvolution.py:37,60-62);
+ *   - `stream` is a cudaStream_t (0 = legacy default stream).  Calls are
+ *     asynchronous and re-entrant; the launch happens on the device that owns
+ *     the output pointer (the calling thread's current device is restored);
+ *   - return 0 on success, a positive cudaError_t on a CUDA failure, a negative
+ *     SSTEM_E_* on bad arguments.  sstem_error_string() explains either.
+ */
+#ifndef SSTEM_B200_H_
+#define SSTEM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSTEM_ABI_VERSION 1
+
+/* argument errors (negative) */
+#define SSTEM_E_NULL      (-1)  /* a required pointer is NULL */
+#define SSTEM_E_SHAPE     (-2)  /* non-positive size / unsupported tap count */
+#define SSTEM_E_ALIGN     (-3)  /* pointer not 4-byte aligned */
+#define SSTEM_E_DEVICE    (-4)  /* pointer is not device memory */
+#define SSTEM_E_FLAG      (-5)  /* unknown flag / mode */
+
+/* flags for the sepconv entry points */
+#define SSTEM_SEPCONV_DEFAULT       0u
+/* evaluate the forward in the reference's exact summation order (fy outer, fx
+ * inner, one accumulator, (in*v) then fma with h -- kernel.cu:45-49): bit-exact
+ * with the reference kernel, ~2x the arithmetic.  Verification mode. */
+#define SSTEM_SEPCONV_STRICT_ORDER  1u
+
+/*
+ * out[b,c,y,x] = sum_{fy,fx} in[b,c,y+fy,x+fx] * v[b,fy,y,x] * h[b,fx,y,x]
+ *
+ * Replaces SeparableConvolution_cuda_forward(THCudaTensor* input, vertical,
+ * horizontal, output) -- libs/sepconv/src/SeparableConvolution_cuda.h:6-11,
+ * launcher libs/sepconv/src/SeparableConvolution_kernel.cu:54-73 -- and the CuPy
+ * launch in sff_scripts_interp/model/sepconv.py:99-109.
+ *   input      [batch, channels, out_h + taps - 1, out_w + taps - 1]
+ *   vertical   [batch, taps, out_h, out_w]
+ *   horizontal [batch, taps, out_h, out_w]
+ *   output     [batch, channels, out_h, out_w]
+ * taps: 1..64 (51 is the reference's only value and the tuned path).
+ */
+int sstem_sepconv_forward(const float* input, const float* vertical, const float* horizontal,
+                          float* output,
+                          int64_t batch, int64_t channels, int64_t out_h, int64_t out_w,
+                          int32_t taps, uint32_t flags, void* stream);
+
+/*
+ * Gradients of the above given grad_output [batch, channels, out_h, out_w].
+ *
+ * Replaces SeparableConvolution_cuda_backward(gradLoss, input, vertical,
+ * horizontal, gradInput, gradVertical, gradHorizontal) --
+ * libs/sepconv/src/SeparableConvolution_cuda.h:13-21, launcher kernel.cu:152-206.
+ * Differences, both deliberate: (1) the channel sum runs over all `channels`
+ * (the reference hard-codes 0,1,2 -- kernel.cu:100-108); (2) grad_input is
+ * actually computed when non-NULL (the reference leaves it zero --
+ * kernel.cu:158 unused, SeparableConvolution.py:60).
+ * Any of the three outputs may be NULL = not wanted (ctx.needs_input_grad).
+ *   grad_input      [batch, channels, out_h + taps - 1, out_w + taps - 1]
+ *   grad_vertical   [batch, taps, out_h, out_w]
+ *   grad_horizontal [batch, taps, out_h, out_w]
+ */
+int sstem_sepconv_backward(const float* grad_output, const float* input,
+                           const float* vertical, const float* horizontal,
+                           float* grad_input, float* grad_vertical, float* grad_horizontal,
+                           int64_t batch, int64_t channels, int64_t out_h, int64_t out_w,
+                           int32_t taps, uint32_t flags, void* stream);
+
+/* memory layout of the warp output */
+#define SSTEM_LAYOUT_NCHW 0
+#define SSTEM_LAYOUT_NHWC 1  /* what the reference materialises (image_warp_torch.py:94,112) */
+
+/*
+ * Zero-padded bilinear backward warp, bit-compatible with
+ * SpatialTransformation.forward(moving_image, deformation_matrix) --
+ * sff_scripts_unfolding/utils/image_warp_torch.py:97-113 (interpolate :32-95):
+ *   out[b,c,i,j] = bilinear(zero-padded moving[b,c], x = j + flow[b,i,j,0],
+ *                                                    y = i + flow[b,i,j,1])
+ * evaluated with the reference's op order and without FMA contraction.
+ *   moving [batch, channels, h, w] contiguous
+ *   flow   logical shape [batch, h, w, 2] addressed through flow_strides[4]
+ *          (in ELEMENTS) -- every reference call site passes a permuted view of
+ *          a planar [batch,2,h,w] tensor (sff_scripts_fusion/inference.py:149)
+ *   out    [batch, channels, h, w] (NCHW) or [batch, h, w, channels] (NHWC)
+ */
+int sstem_warp_forward(const float* moving, const float* flow, const int64_t flow_strides[4],
+                       float* out,
+                       int64_t batch, int64_t channels, int64_t h, int64_t w,
+                       int32_t out_layout, void* stream);
+
+/* pixel type of the numpy-semantics warp input */
+#define SSTEM_PIX_U8  0
+#define SSTEM_PIX_F32 1
+#define SSTEM_WARP_BILINEAR 0
+#define SSTEM_WARP_NEAREST  1
+
+/*
+ * Clamp-border backward warp with the semantics of numpy
+ * image_warp(im, flow, mode) -- simu_sff/image_warp.py:3-111 (identical copies
+ * under sff_scripts_{unfolding,fusion}/utils/): NHWC image, x1 = clip(x0+1)
+ * taken from the clipped x0 (:84-88), weights from frac(flow) (:72-82),
+ * 'nearest' = floor (:67-69), result truncated to uint8 (:110).
+ *   im        [batch, h, w, channels], uint8 or float32 (pix_type)
+ *   flow      [batch, h, w, 2] float32 contiguous (ch0 = x, ch1 = y)
+ *   out_u8    [batch, h, w, channels] uint8, may be NULL
+ *   out_f32   [batch, h, w, channels] value before the uint8 cast, may be NULL
+ */
+int sstem_image_warp(const void* im, int32_t pix_type, const float* flow,
+                     uint8_t* out_u8, float* out_f32,
+                     int64_t batch, int64_t h, int64_t w, int64_t channels,
+                     int32_t mode, void* stream);
+
+/*
+ * FP32 FMA-pipe probe: runs a register-resident FFMA loop on every SM of the
+ * current device and returns the sustained rate in TFLOP/s (2 flop per FMA).
+ * bench.py uses it as the measured denominator of the sepconv roofline
+ * (MEASURED_PEAKS.json has no fp32 row).  Synchronous.
+ */
+int sstem_fp32_peak_probe(double* tflops_out, double* sm_mhz_out);
+
+/* counts kernel launches issued through this library by the calling process */
+int64_t sstem_launch_count(void);
+
+int sstem_abi_version(void);
+const char* sstem_error_string(int code);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSTEM_B200_H_ */

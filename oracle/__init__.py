@@ -1,0 +1,253 @@
+"""ORACLE -- TEST INFRASTRUCTURE ONLY.
+
+CPU restatement of the reference's hot path (sydeng99/ssTEM-restoration):
+the 51-tap adaptive separable local convolution (``libs/sepconv``) and the two
+flow-driven bilinear backward warps (``image_warp_torch.SpatialTransformation``
+and numpy ``image_warp``).  Only ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import this
+package, and only as the checker or as the CPU baseline -- the product package
+``sstem_restoration_b200`` never does.
+
+Parity pins (see tests/golden/README.md):
+  * warp restatements: bit-checked against the reference's own Python
+    (imported from /root/reference in the build container) -- fixtures
+    ``tests/golden/warp_*.npz`` made by ``tests/golden/make_golden.py``.
+  * sepconv fp32 "reforder" restatement: checked against the reference's own
+    ``.cu`` compiled verbatim for sm_100a (``oracle/_ref``) and run on a B200 --
+    fixtures ``tests/golden/sepconv_ref_*.npz`` made by
+    ``tests/golden/make_sepconv_ref_golden.py``.
+  * grad w.r.t. input has no reference implementation (the reference returns
+    zeros, ``libs/sepconv/SeparableConvolution.py:60``): its oracle is the
+    mathematical adjoint in fp64, cross-checked with torch autograd --
+    "parity unpinned" for that one output.
+
+All file:line citations are relative to the reference checkout.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force: bool = False) -> str:
+    """Compile oracle/liboracle.so (and oracle/_ref when the reference is mounted)."""
+    so = os.path.join(_HERE, "liboracle.so")
+    src = os.path.join(_HERE, "sepconv_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", _HERE, "all"], check=True, capture_output=True)
+    return so
+
+
+def _lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = ctypes.CDLL(build())
+    return _LIB
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+def _dims(inp, v):
+    B, C, IH, IW = inp.shape
+    Bv, K, H, W = v.shape
+    assert B == Bv and IH == H + K - 1 and IW == W + K - 1, (inp.shape, v.shape)
+    assert K <= 128
+    return (ctypes.c_int64(B), ctypes.c_int64(C), ctypes.c_int64(H), ctypes.c_int64(W), ctypes.c_int(K)), (B, C, H, W, K)
+
+
+# --------------------------------------------------------------------------- sepconv
+def sepconv_forward_reforder(inp, v, h):
+    """fp32, the reference's summation order (kernel.cu:38-51: fy outer, fx inner,
+    one accumulator, FMUL(in,v) then FFMA(.,h,acc))."""
+    inp, v, h = _f32(inp), _f32(v), _f32(h)
+    d, (B, C, H, W, K) = _dims(inp, v)
+    out = np.empty((B, C, H, W), np.float32)
+    _lib().oracle_sepconv_fwd_reforder(_p(inp), _p(v), _p(h), _p(out), *d)
+    return out
+
+
+def sepconv_forward_f64(inp, v, h):
+    """fp64 accumulation of the same sum: the 'truth' for protocol P2."""
+    inp, v, h = _f32(inp), _f32(v), _f32(h)
+    d, (B, C, H, W, K) = _dims(inp, v)
+    out = np.empty((B, C, H, W), np.float64)
+    _lib().oracle_sepconv_fwd_f64(_p(inp), _p(v), _p(h), _p(out), *d)
+    return out
+
+
+def sepconv_grad_vertical_reforder(g, inp, h):
+    """kernel.cu:77-112, channel sum generalised from the literal 0,1,2 to C."""
+    g, inp, h = _f32(g), _f32(inp), _f32(h)
+    d, (B, C, H, W, K) = _dims(inp, h)
+    gv = np.empty((B, K, H, W), np.float32)
+    _lib().oracle_sepconv_gradv_reforder(_p(g), _p(inp), _p(h), _p(gv), *d)
+    return gv
+
+
+def sepconv_grad_horizontal_reforder(g, inp, v):
+    """kernel.cu:115-150, channel sum generalised to C."""
+    g, inp, v = _f32(g), _f32(inp), _f32(v)
+    d, (B, C, H, W, K) = _dims(inp, v)
+    gh = np.empty((B, K, H, W), np.float32)
+    _lib().oracle_sepconv_gradh_reforder(_p(g), _p(inp), _p(v), _p(gh), *d)
+    return gh
+
+
+def sepconv_grad_taps_f64(g, inp, v, h):
+    g, inp, v, h = _f32(g), _f32(inp), _f32(v), _f32(h)
+    d, (B, C, H, W, K) = _dims(inp, v)
+    gv = np.empty((B, K, H, W), np.float64)
+    gh = np.empty((B, K, H, W), np.float64)
+    _lib().oracle_sepconv_gradvh_f64(_p(g), _p(inp), _p(v), _p(h), _p(gv), _p(gh), *d)
+    return gv, gh
+
+
+def sepconv_grad_input_f64(g, v, h):
+    """Adjoint of the forward (no reference implementation)."""
+    g, v, h = _f32(g), _f32(v), _f32(h)
+    B, C, H, W = g.shape
+    K = v.shape[1]
+    gi = np.empty((B, C, H + K - 1, W + K - 1), np.float64)
+    _lib().oracle_sepconv_gradin_f64(_p(g), _p(v), _p(h), _p(gi), None,
+                                     ctypes.c_int64(B), ctypes.c_int64(C), ctypes.c_int64(H),
+                                     ctypes.c_int64(W), ctypes.c_int(K))
+    return gi
+
+
+def sepconv_fwd_bwd_fast(inp, v, h, g=None):
+    """Factored fp32 CPU port, OpenMP over pixels: the cpu_baseline ('port')."""
+    inp, v, h = _f32(inp), _f32(v), _f32(h)
+    d, (B, C, H, W, K) = _dims(inp, v)
+    out = np.empty((B, C, H, W), np.float32)
+    if g is None:
+        _lib().oracle_sepconv_fwd_bwd_fast(None, _p(inp), _p(v), _p(h), _p(out), None, None, *d)
+        return out
+    g = _f32(g)
+    gv = np.empty((B, K, H, W), np.float32)
+    gh = np.empty((B, K, H, W), np.float32)
+    _lib().oracle_sepconv_fwd_bwd_fast(_p(g), _p(inp), _p(v), _p(h), _p(out), _p(gv), _p(gh), *d)
+    return out, gv, gh
+
+
+def sepconv_unfold_torch(inp, v, h):
+    """The CPU baseline BASELINE.json names for sepconv: an unfold-based torch-CPU
+    evaluation of kernel.cu:45-49 (row windows dotted with h, then with v,
+    accumulated over fy).  Differentiable, so fwd+bwd is timed through autograd."""
+    import torch
+
+    K = v.shape[1]
+    H, W = v.shape[2], v.shape[3]
+    out = None
+    for fy in range(K):
+        rows = inp[:, :, fy:fy + H, :]                      # [B,C,H,W+K-1]
+        win = rows.unfold(3, K, 1)                          # [B,C,H,W,K]
+        r = (win * h.permute(0, 2, 3, 1).unsqueeze(1)).sum(-1)
+        term = r * v[:, fy].unsqueeze(1)
+        out = term if out is None else out + term
+    return out
+
+
+# --------------------------------------------------------------------------- warps
+def warp_torch_restated(moving, flow):
+    """numpy-fp32 restatement of SpatialTransformation.forward
+    (sff_scripts_unfolding/utils/image_warp_torch.py:97-113, interpolate :32-95).
+
+    moving [B,C,H,W] float32, flow [B,H,W,2] float32 (ch0 = x, ch1 = y) ->
+    [B,C,H,W] float32.  Op order kept: x = (fx + j) + 1; x0 = floor(x); x1 = x0+1;
+    clamp both to [0, W+1] (the 1-px zero-padded image); dx = float(x1c) - x;
+    wa = dx*dy, wb = dx*(1-dy), wc = (1-dx)*dy, wd = (1-dx)*(1-dy);
+    out = ((wa*Ia + wb*Ib) + wc*Ic) + wd*Id with Ia=(y0,x0) Ib=(y1,x0) Ic=(y0,x1) Id=(y1,x1).
+    """
+    moving = _f32(moving)
+    flow = np.asarray(flow, dtype=np.float32)
+    B, C, H, W = moving.shape
+    one = np.float32(1.0)
+    jj = np.arange(W, dtype=np.float32)[None, None, :]
+    ii = np.arange(H, dtype=np.float32)[None, :, None]
+    x = (flow[..., 0] + jj) + one
+    y = (flow[..., 1] + ii) + one
+    x0 = np.floor(x).astype(np.int64)
+    y0 = np.floor(y).astype(np.int64)
+    x1 = x0 + 1
+    y1 = y0 + 1
+    x0 = np.clip(x0, 0, W + 1); x1 = np.clip(x1, 0, W + 1)
+    y0 = np.clip(y0, 0, H + 1); y1 = np.clip(y1, 0, H + 1)
+    dx = x1.astype(np.float32) - x
+    dy = y1.astype(np.float32) - y
+    wa = dx * dy
+    wb = dx * (one - dy)
+    wc = (one - dx) * dy
+    wd = (one - dx) * (one - dy)
+    pad = np.zeros((B, C, H + 2, W + 2), np.float32)
+    pad[:, :, 1:-1, 1:-1] = moving
+    bi = np.arange(B)[:, None, None]
+    out = np.empty((B, C, H, W), np.float32)
+    for c in range(C):
+        pc = pad[:, c]
+        Ia = pc[bi, y0, x0]; Ib = pc[bi, y1, x0]; Ic = pc[bi, y0, x1]; Id = pc[bi, y1, x1]
+        out[:, c] = ((wa * Ia + wb * Ib) + wc * Ic) + wd * Id
+    return out
+
+
+def image_warp_restated(im, flow, mode="bilinear", return_float=False):
+    """Restatement of numpy image_warp (simu_sff/image_warp.py:3-111).
+
+    im ndim 2/3/4 = [[B],H,W,[C]], flow [[B],H,W,2].  x0 = clip(j + floor(fx), 0, W-1);
+    x1 = clip(x0 + 1, 0, W-1) computed from the CLIPPED x0 (:84-88); weights from
+    frac(flow) regardless of clipping (:72-82); 'nearest' samples (y0,x0), i.e.
+    floor (:67-69); result truncated to uint8 (:110).  `return_float` also returns
+    the value before the cast (used for bit-parity of the CUDA kernel).
+    """
+    im = np.asarray(im)
+    flow = np.asarray(flow)
+    nd = im.ndim
+    if nd == 2:
+        im4, fl4 = im[None, :, :, None], flow[None]
+    elif nd == 3:
+        im4, fl4 = im[None], flow[None]
+    elif nd == 4:
+        im4, fl4 = im, flow
+    else:
+        raise AttributeError("The dimension of im must be 2, 3 or 4")
+    B, H, W, C = im4.shape
+    fl_floor = np.floor(fl4)
+    fi = fl_floor.astype(np.int32)
+    jj = np.arange(W)[None, None, :]
+    ii = np.arange(H)[None, :, None]
+    x0 = np.clip(jj + fi[..., 0], 0, W - 1)
+    y0 = np.clip(ii + fi[..., 1], 0, H - 1)
+    bi = np.arange(B)[:, None, None]
+    if mode == "nearest":
+        val = im4[bi, y0, x0]
+    elif mode == "bilinear":
+        frac = fl4 - fl_floor
+        xw = frac[..., 0][..., None]
+        yw = frac[..., 1][..., None]
+        x1 = np.clip(x0 + 1, 0, W - 1)
+        y1 = np.clip(y0 + 1, 0, H - 1)
+        wa = (1 - xw) * (1 - yw)
+        wb = (1 - xw) * yw
+        wc = xw * (1 - yw)
+        wd = xw * yw
+        val = wa * im4[bi, y0, x0] + wb * im4[bi, y1, x0] + wc * im4[bi, y0, x1] + wd * im4[bi, y1, x1]
+    else:
+        raise UnboundLocalError("mode must be 'nearest' or 'bilinear'")
+    valf = val
+    if nd == 2:
+        valf = np.squeeze(valf)
+    elif nd == 3:
+        valf = np.squeeze(valf, axis=0)
+    u8 = valf.astype(np.uint8)
+    return (u8, valf) if return_float else u8

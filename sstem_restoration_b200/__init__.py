@@ -1,0 +1,25 @@
+"""sstem_restoration_b200 -- B200-native (sm_100a) hot path of ssTEM-restoration.
+
+The package holds only what the path needs: the CUDA kernels and C ABI (csrc/,
+include/sstem_b200.h), and the host-side mirrors of the reference's operator
+interfaces:
+
+    from sstem_restoration_b200 import SeparableConvolution          # libs/sepconv
+    from sstem_restoration_b200 import FunctionSepconv, ModuleSepconv  # model/sepconv.py
+    from sstem_restoration_b200 import SpatialTransformation, image_warp
+
+There is no CPU / PyTorch fallback: without libsstem_b200.so (see
+__graft_entry__.build) every operator raises.
+"""
+from ._lib import SstemError, launch_count, fp32_peak_probe  # noqa: F401
+from .sepconv import (  # noqa: F401
+    SeparableConvolution, FunctionSepconv, ModuleSepconv, set_strict_order,
+)
+from .warp import SpatialTransformation, image_warp  # noqa: F401
+from . import shard, synth  # noqa: F401
+
+__all__ = [
+    "SeparableConvolution", "FunctionSepconv", "ModuleSepconv", "set_strict_order",
+    "SpatialTransformation", "image_warp", "SstemError", "launch_count", "fp32_peak_probe",
+    "shard", "synth",
+]

@@ -1,0 +1,91 @@
+"""ctypes binding of the C ABI declared in include/sstem_b200.h.
+
+This is the only way the package computes anything: if the shared library is
+missing (or was not built for this GPU) every call raises -- there is no CPU,
+PyTorch-eager or oracle fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+from ._build import LIB_PATH
+
+_c_i64 = ctypes.c_int64
+_c_i32 = ctypes.c_int32
+_c_u32 = ctypes.c_uint32
+_c_p = ctypes.c_void_p
+
+SEPCONV_DEFAULT = 0
+SEPCONV_STRICT_ORDER = 1
+LAYOUT_NCHW = 0
+LAYOUT_NHWC = 1
+PIX_U8 = 0
+PIX_F32 = 1
+WARP_BILINEAR = 0
+WARP_NEAREST = 1
+
+#: every symbol include/sstem_b200.h declares (tests check the library exports all of them)
+EXPORTED_SYMBOLS = (
+    "sstem_sepconv_forward", "sstem_sepconv_backward", "sstem_warp_forward", "sstem_image_warp",
+    "sstem_fp32_peak_probe", "sstem_launch_count", "sstem_abi_version", "sstem_error_string",
+)
+
+_lock = threading.Lock()
+_lib = None
+
+
+class SstemError(RuntimeError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise SstemError(
+                f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  sstem_restoration_b200 has no CPU fallback."
+            )
+        lib = ctypes.CDLL(LIB_PATH)
+        lib.sstem_sepconv_forward.argtypes = [_c_p, _c_p, _c_p, _c_p, _c_i64, _c_i64, _c_i64, _c_i64, _c_i32, _c_u32, _c_p]
+        lib.sstem_sepconv_forward.restype = ctypes.c_int
+        lib.sstem_sepconv_backward.argtypes = [_c_p] * 7 + [_c_i64] * 4 + [_c_i32, _c_u32, _c_p]
+        lib.sstem_sepconv_backward.restype = ctypes.c_int
+        lib.sstem_warp_forward.argtypes = [_c_p, _c_p, ctypes.POINTER(_c_i64), _c_p, _c_i64, _c_i64, _c_i64, _c_i64, _c_i32, _c_p]
+        lib.sstem_warp_forward.restype = ctypes.c_int
+        lib.sstem_image_warp.argtypes = [_c_p, _c_i32, _c_p, _c_p, _c_p, _c_i64, _c_i64, _c_i64, _c_i64, _c_i32, _c_p]
+        lib.sstem_image_warp.restype = ctypes.c_int
+        lib.sstem_fp32_peak_probe.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+        lib.sstem_fp32_peak_probe.restype = ctypes.c_int
+        lib.sstem_launch_count.argtypes = []
+        lib.sstem_launch_count.restype = _c_i64
+        lib.sstem_abi_version.argtypes = []
+        lib.sstem_abi_version.restype = ctypes.c_int
+        lib.sstem_error_string.argtypes = [ctypes.c_int]
+        lib.sstem_error_string.restype = ctypes.c_char_p
+        _lib = lib
+    return _lib
+
+
+def check(code: int, what: str) -> None:
+    if code != 0:
+        msg = load().sstem_error_string(code).decode()
+        raise SstemError(f"{what} failed with code {code}: {msg}")
+
+
+def launch_count() -> int:
+    return int(load().sstem_launch_count())
+
+
+def fp32_peak_probe():
+    """(TFLOP/s, SM MHz) of a register-resident FFMA loop on the current device."""
+    t = ctypes.c_double(0.0)
+    m = ctypes.c_double(0.0)
+    check(load().sstem_fp32_peak_probe(ctypes.byref(t), ctypes.byref(m)), "sstem_fp32_peak_probe")
+    return t.value, m.value

@@ -1,0 +1,76 @@
+// C-ABI entry points for the sepconv path (argument checks + dispatch) and the
+// small ABI utilities.  See include/sstem_b200.h for the contract.
+#include "common.cuh"
+
+namespace sstem {
+std::atomic<int64_t> g_launches{0};
+}
+using namespace sstem;
+
+static int check_sepconv_dims(int64_t B, int64_t C, int64_t H, int64_t W, int K) {
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return SSTEM_E_SHAPE;
+    if (K < 1 || K > 64) return SSTEM_E_SHAPE;
+    if (H + K - 1 > INT32_MAX / 2 || W + K - 1 > INT32_MAX / 2 || C > 65535) return SSTEM_E_SHAPE;
+    return 0;
+}
+
+extern "C" int sstem_sepconv_forward(const float* input, const float* vertical, const float* horizontal,
+                                     float* output, int64_t B, int64_t C, int64_t H, int64_t W,
+                                     int32_t K, uint32_t flags, void* stream) {
+    if (!input || !vertical || !horizontal || !output) return SSTEM_E_NULL;
+    if (int e = check_sepconv_dims(B, C, H, W, K)) return e;
+    if (flags & ~SSTEM_SEPCONV_STRICT_ORDER) return SSTEM_E_FLAG;
+    if (!aligned4(input) || !aligned4(vertical) || !aligned4(horizontal) || !aligned4(output)) return SSTEM_E_ALIGN;
+    DeviceGuard guard(output);
+    if (guard.err) return guard.err;
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool strict = flags & SSTEM_SEPCONV_STRICT_ORDER;
+    if (K == 51 && !strict) return launch_sepconv_fwd_k51(input, vertical, horizontal, output, B, C, H, W, s);
+    return launch_sepconv_fwd_generic(input, vertical, horizontal, output, B, C, H, W, K, strict, s);
+}
+
+extern "C" int sstem_sepconv_backward(const float* grad_output, const float* input,
+                                      const float* vertical, const float* horizontal,
+                                      float* grad_input, float* grad_vertical, float* grad_horizontal,
+                                      int64_t B, int64_t C, int64_t H, int64_t W,
+                                      int32_t K, uint32_t flags, void* stream) {
+    if (!grad_output || !input || !vertical || !horizontal) return SSTEM_E_NULL;
+    if (!grad_input && !grad_vertical && !grad_horizontal) return SSTEM_E_NULL;
+    if (int e = check_sepconv_dims(B, C, H, W, K)) return e;
+    if (flags & ~SSTEM_SEPCONV_STRICT_ORDER) return SSTEM_E_FLAG;
+    if (!aligned4(grad_output) || !aligned4(input) || !aligned4(vertical) || !aligned4(horizontal) ||
+        !aligned4(grad_input) || !aligned4(grad_vertical) || !aligned4(grad_horizontal))
+        return SSTEM_E_ALIGN;
+    const void* any_out = grad_vertical ? grad_vertical : (grad_horizontal ? grad_horizontal : grad_input);
+    DeviceGuard guard(any_out);
+    if (guard.err) return guard.err;
+    cudaStream_t s = (cudaStream_t)stream;
+    int e = 0;
+    if (grad_vertical || grad_horizontal) {
+        if (K == 51)
+            e = launch_sepconv_bwd_taps_k51(grad_output, input, vertical, horizontal, grad_vertical, grad_horizontal, B, C, H, W, s);
+        else
+            e = launch_sepconv_bwd_taps_generic(grad_output, input, vertical, horizontal, grad_vertical, grad_horizontal, B, C, H, W, K, s);
+        if (e) return e;
+    }
+    if (grad_input)
+        e = launch_sepconv_bwd_input_generic(grad_output, vertical, horizontal, grad_input, B, C, H, W, K, s);
+    return e;
+}
+
+extern "C" int64_t sstem_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+extern "C" int sstem_abi_version(void) { return SSTEM_ABI_VERSION; }
+
+extern "C" const char* sstem_error_string(int code) {
+    switch (code) {
+        case 0: return "success";
+        case SSTEM_E_NULL: return "sstem: a required pointer is NULL";
+        case SSTEM_E_SHAPE: return "sstem: non-positive size or unsupported tap count (1..64)";
+        case SSTEM_E_ALIGN: return "sstem: pointer is not sufficiently aligned";
+        case SSTEM_E_DEVICE: return "sstem: pointer is not CUDA device memory";
+        case SSTEM_E_FLAG: return "sstem: unknown flag, layout or mode";
+        default: break;
+    }
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "sstem: unknown error code";
+}

@@ -1,0 +1,64 @@
+// Shared host-side helpers for the C-ABI translation units (no torch, no THC).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <atomic>
+
+#include "../../include/sstem_b200.h"
+
+namespace sstem {
+
+extern std::atomic<int64_t> g_launches;
+
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// Switches the calling thread to the device that owns `ptr` for the lifetime of
+// the guard (nn.DataParallel replica threads call in with their own current
+// device, but a stray call from another thread must still land correctly).
+struct DeviceGuard {
+    int prev = -1;
+    int err = 0;
+    explicit DeviceGuard(const void* ptr) {
+        cudaPointerAttributes at;
+        cudaError_t e = cudaPointerGetAttributes(&at, ptr);
+        if (e != cudaSuccess) { cudaGetLastError(); err = SSTEM_E_DEVICE; return; }
+        if (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged) { err = SSTEM_E_DEVICE; return; }
+        int cur = 0;
+        cudaGetDevice(&cur);
+        if (cur != at.device) { prev = cur; cudaSetDevice(at.device); }
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+inline bool aligned4(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 3u) == 0; }
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+inline int sm_count() {
+    static thread_local int cached_dev = -1, cached = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev != cached_dev) {
+        cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
+        cached_dev = dev;
+    }
+    return cached;
+}
+
+inline int finish_launch() { return (int)cudaGetLastError(); }
+
+// ---- launchers implemented in the per-op translation units -----------------
+int launch_sepconv_fwd_generic(const float* in, const float* v, const float* h, float* out,
+                               int64_t B, int64_t C, int64_t H, int64_t W, int K, bool strict,
+                               cudaStream_t s);
+int launch_sepconv_fwd_k51(const float* in, const float* v, const float* h, float* out,
+                           int64_t B, int64_t C, int64_t H, int64_t W, cudaStream_t s);
+int launch_sepconv_bwd_taps_generic(const float* g, const float* in, const float* v, const float* h,
+                                    float* gv, float* gh,
+                                    int64_t B, int64_t C, int64_t H, int64_t W, int K, cudaStream_t s);
+int launch_sepconv_bwd_taps_k51(const float* g, const float* in, const float* v, const float* h,
+                                float* gv, float* gh,
+                                int64_t B, int64_t C, int64_t H, int64_t W, cudaStream_t s);
+int launch_sepconv_bwd_input_generic(const float* g, const float* v, const float* h, float* gi,
+                                     int64_t B, int64_t C, int64_t H, int64_t W, int K, cudaStream_t s);
+
+}  // namespace sstem

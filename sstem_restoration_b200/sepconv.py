@@ -1,0 +1,144 @@
+"""Adaptive separable local convolution: the reference's operator interface over
+the sm_100a C ABI.
+
+Mirrors, name for name and argument for argument,
+  * ``SeparableConvolution`` (torch.autograd.Function) --
+    libs/sepconv/SeparableConvolution.py:11-78 of the reference, and
+  * ``FunctionSepconv`` / ``ModuleSepconv`` -- sff_scripts_interp/model/sepconv.py:152-164,
+so ``IFNet`` (sff_scripts_interp/model/model_interp.py:47,94; sp_scripts_train/networks.py:70,120-123)
+can bind ``self.separable_conv = SeparableConvolution.apply`` unchanged.
+
+Behaviour kept: the shape / tap-count / contiguity ``assert``s
+(SeparableConvolution.py:29-35), ``NotImplementedError`` for CPU tensors (:47-48),
+a freshly allocated output on the input's device, a 3-tuple from backward.
+Behaviour fixed (documented in include/sstem_b200.h): the backward channel sum
+covers all C (the reference hard-codes 3), grad w.r.t. input is really computed
+when requested (the reference returns zeros), ``needs_input_grad`` is honoured,
+outputs are not redundantly zero-filled.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+
+from . import _lib
+
+_STRICT = os.environ.get("SSTEM_SEPCONV_STRICT", "0") not in ("", "0")
+
+
+def set_strict_order(enabled: bool) -> None:
+    """Evaluate the forward in the reference's exact fp32 summation order
+    (bit-equal to kernel.cu:45-49; verification mode, slower)."""
+    global _STRICT
+    _STRICT = bool(enabled)
+
+
+def _flags() -> int:
+    return _lib.SEPCONV_STRICT_ORDER if _STRICT else _lib.SEPCONV_DEFAULT
+
+
+def _stream_ptr(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _check_shapes(input, vertical, horizontal, filter_size=None):
+    intInputHeight = input.size(2)
+    intInputWidth = input.size(3)
+    intFilterSize = min(vertical.size(1), horizontal.size(1))
+    intOutputHeight = min(vertical.size(2), horizontal.size(2))
+    intOutputWidth = min(vertical.size(3), horizontal.size(3))
+    want = intFilterSize if filter_size is None else filter_size
+    assert (intInputHeight - want == intOutputHeight - 1)
+    assert (intInputWidth - want == intOutputWidth - 1)
+    if filter_size is not None:
+        assert (intFilterSize == filter_size)
+    assert (input.is_contiguous() == True)
+    assert (vertical.is_contiguous() == True)
+    assert (horizontal.is_contiguous() == True)
+    return intFilterSize, intOutputHeight, intOutputWidth
+
+
+def _forward_impl(input, vertical, horizontal, filter_size):
+    K, oh, ow = _check_shapes(input, vertical, horizontal, filter_size)
+    if input.is_cuda == False:
+        raise NotImplementedError()  # as the reference: CPU version not implemented
+    if not (vertical.is_cuda and horizontal.is_cuda):
+        raise NotImplementedError()
+    if input.dtype != torch.float32 or vertical.dtype != torch.float32 or horizontal.dtype != torch.float32:
+        raise TypeError("sepconv: float32 tensors required (the reference op is THCudaTensor = float)")
+    assert vertical.shape == horizontal.shape, "vertical and horizontal must have the same shape"
+    assert vertical.size(0) == input.size(0), "batch mismatch"
+    B, C = input.size(0), input.size(1)
+    output = torch.empty((B, C, oh, ow), dtype=input.dtype, device=input.device)
+    if output.numel() == 0:
+        return output
+    with torch.cuda.device_of(input):
+        code = _lib.load().sstem_sepconv_forward(
+            input.data_ptr(), vertical.data_ptr(), horizontal.data_ptr(), output.data_ptr(),
+            B, C, oh, ow, K, _flags(), _stream_ptr(input))
+    _lib.check(code, "sstem_sepconv_forward")
+    return output
+
+
+def _backward_impl(ctx, grad_output):
+    input, vertical, horizontal = ctx.saved_tensors
+    need_in, need_v, need_h = ctx.needs_input_grad[:3]
+    B, C = input.size(0), input.size(1)
+    K, oh, ow = vertical.size(1), vertical.size(2), vertical.size(3)
+    grad_output = grad_output.contiguous()
+    if grad_output.is_cuda == False:
+        raise NotImplementedError()
+    grad_input = torch.empty_like(input) if need_in else None
+    grad_vertical = torch.empty_like(vertical) if need_v else None
+    grad_horizontal = torch.empty_like(horizontal) if need_h else None
+    if (need_in or need_v or need_h) and grad_output.numel() > 0:
+        with torch.cuda.device_of(input):
+            code = _lib.load().sstem_sepconv_backward(
+                grad_output.data_ptr(), input.data_ptr(), vertical.data_ptr(), horizontal.data_ptr(),
+                grad_input.data_ptr() if need_in else None,
+                grad_vertical.data_ptr() if need_v else None,
+                grad_horizontal.data_ptr() if need_h else None,
+                B, C, oh, ow, K, _flags(), _stream_ptr(input))
+        _lib.check(code, "sstem_sepconv_backward")
+    return grad_input, grad_vertical, grad_horizontal
+
+
+class SeparableConvolution(torch.autograd.Function):
+    """Drop-in for libs/sepconv/SeparableConvolution.py:11-78 (51 taps, asserted)."""
+
+    @staticmethod
+    def forward(context, input, vertical, horizontal):
+        context.save_for_backward(input, vertical, horizontal)
+        return _forward_impl(input, vertical, horizontal, 51)
+
+    @staticmethod
+    def backward(context, grad_output):
+        return _backward_impl(context, grad_output)
+
+
+class _FunctionSepconv(torch.autograd.Function):
+    """Drop-in for sff_scripts_interp/model/sepconv.py:76-150: tap count taken from
+    the tensors (:83), and -- unlike the reference, whose backward raises
+    NotImplementedError (:140-146) -- differentiable."""
+
+    @staticmethod
+    def forward(self, input, vertical, horizontal):
+        self.save_for_backward(input, vertical, horizontal)
+        return _forward_impl(input, vertical, horizontal, None)
+
+    @staticmethod
+    def backward(self, gradOutput):
+        return _backward_impl(self, gradOutput)
+
+
+def FunctionSepconv(tenInput, tenVertical, tenHorizontal):
+    return _FunctionSepconv.apply(tenInput, tenVertical, tenHorizontal)
+
+
+class ModuleSepconv(torch.nn.Module):
+    def __init__(self):
+        super(ModuleSepconv, self).__init__()
+
+    def forward(self, tenInput, tenVertical, tenHorizontal):
+        return _FunctionSepconv.apply(tenInput, tenVertical, tenHorizontal)

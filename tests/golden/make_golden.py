@@ -1,0 +1,83 @@
+"""Generates tests/golden/warp_*.npz and flow_*.npz by running the REFERENCE's own
+Python (imported from /root/reference; only possible in the build container).
+
+    python tests/golden/make_golden.py
+
+Fixtures hold the seeded inputs' parameters and the reference outputs; tests
+rebuild the inputs from the seeds, run the oracle restatement (CPU) and the CUDA
+kernels (GPU) and require bit-equality.  Reference functions exercised:
+  * simu_sff/image_warp.py:3-111                         image_warp
+  * sff_scripts_unfolding/utils/image_warp_torch.py:5-113 SpatialTransformation
+  * simu_sff/flow_synthesis.py:13-83                      gen_line, gen_flow
+    (imported with a stub `matplotlib` because flow_synthesis.py:6 imports pyplot)
+"""
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = os.environ.get("SSTEM_REFERENCE", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
+
+from tests.golden import cases  # noqa: E402
+
+
+def _load(path, name, extra_path=None):
+    if extra_path:
+        sys.path.insert(0, extra_path)
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    if extra_path:
+        sys.path.remove(extra_path)
+    return mod
+
+
+def main():
+    ref_np = _load(os.path.join(REF, "simu_sff", "image_warp.py"), "ref_image_warp")
+    ref_t = _load(os.path.join(REF, "sff_scripts_unfolding", "utils", "image_warp_torch.py"), "ref_image_warp_torch")
+    # flow_synthesis imports matplotlib.pyplot and PIL at module level; stub what is absent
+    for name in ("matplotlib", "matplotlib.pyplot"):
+        if name not in sys.modules:
+            try:
+                __import__(name)
+            except Exception:
+                sys.modules[name] = types.ModuleType(name)
+    ref_fs = _load(os.path.join(REF, "simu_sff", "flow_synthesis.py"), "ref_flow_synthesis",
+                   extra_path=os.path.join(REF, "simu_sff"))
+
+    # ---- numpy image_warp ----------------------------------------------------------
+    out = {}
+    for name, (im, flow, mode) in cases.image_warp_cases().items():
+        out[name] = ref_np.image_warp(im, flow, mode)
+    np.savez_compressed(os.path.join(HERE, "warp_numpy_ref.npz"), **out)
+    print("image_warp cases:", {k: v.shape for k, v in out.items()})
+
+    # ---- torch SpatialTransformation (CPU run of the reference) ----------------------
+    out = {}
+    st = ref_t.SpatialTransformation(use_gpu=False)
+    for name, (moving, flow) in cases.warp_torch_cases().items():
+        with torch.no_grad():
+            o = st(torch.from_numpy(moving), torch.from_numpy(flow))
+        out[name] = o.contiguous().numpy()
+    np.savez_compressed(os.path.join(HERE, "warp_torch_ref.npz"), **out)
+    print("SpatialTransformation cases:", {k: v.shape for k, v in out.items()})
+
+    # ---- gen_line / gen_flow ----------------------------------------------------------
+    out = {}
+    for name, (h, w, p1, p2, lw, fw, dk) in cases.gen_flow_cases().items():
+        k, b = ref_fs.gen_line(p1, p2)
+        flow, mask = ref_fs.gen_flow(h, w, k, b, lw, fw, dk)
+        out[name + "_kb"] = np.array([k, b], np.float64)
+        out[name + "_flow"] = flow
+        out[name + "_mask"] = mask.astype(np.uint8)
+    np.savez_compressed(os.path.join(HERE, "gen_flow_ref.npz"), **out)
+    print("gen_flow cases:", [k for k in out if k.endswith("_flow")])
+
+
+if __name__ == "__main__":
+    main()

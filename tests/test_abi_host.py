@@ -1,0 +1,142 @@
+"""CPU: the C-ABI library loads and exports what include/*.h declares; host-side logic."""
+import ctypes
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "sstem_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(sstem_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    lib = ctypes.CDLL(built_lib)
+    declared = _declared_symbols()
+    assert len(declared) >= 8
+    for sym in declared:
+        assert hasattr(lib, sym), f"{sym} declared in include/sstem_b200.h but not exported"
+    from sstem_restoration_b200 import _lib
+    assert sorted(_lib.EXPORTED_SYMBOLS) == declared
+
+
+def test_abi_version_and_error_strings(built_lib):
+    from sstem_restoration_b200 import _lib
+    lib = _lib.load()
+    assert lib.sstem_abi_version() == 1
+    assert lib.sstem_error_string(0) == b"success"
+    for code in (-1, -2, -3, -4, -5):
+        assert lib.sstem_error_string(code).startswith(b"sstem:")
+    assert lib.sstem_launch_count() >= 0
+
+
+def test_argument_errors_do_not_need_a_gpu(built_lib):
+    from sstem_restoration_b200 import _lib
+    lib = _lib.load()
+    assert lib.sstem_sepconv_forward(None, None, None, None, 1, 1, 1, 1, 51, 0, None) == -1
+    buf = ctypes.create_string_buffer(64)
+    p = ctypes.addressof(buf)
+    assert lib.sstem_sepconv_forward(p, p, p, p, 0, 3, 4, 4, 51, 0, None) == -2
+    assert lib.sstem_sepconv_forward(p, p, p, p, 1, 3, 4, 4, 65, 0, None) == -2
+    assert lib.sstem_sepconv_forward(p, p, p, p, 1, 3, 4, 4, 51, 8, None) == -5
+    assert lib.sstem_sepconv_forward(p + 1, p, p, p, 1, 3, 4, 4, 51, 0, None) == -3
+    assert lib.sstem_sepconv_backward(p, p, p, p, None, None, None, 1, 3, 4, 4, 51, 0, None) == -1
+    strides = (ctypes.c_int64 * 4)(32, 8, 2, 1)
+    assert lib.sstem_warp_forward(p, p, strides, p, 1, 1, 2, 2, 7, None) == -5
+    assert lib.sstem_image_warp(p, 9, p, p, None, 1, 2, 2, 1, 0, None) == -5
+    with pytest.raises(_lib.SstemError):
+        _lib.check(-2, "x")
+
+
+def test_sepconv_asserts_and_cpu_error_mirror_reference(built_lib):
+    """libs/sepconv/SeparableConvolution.py:29-35 asserts, :47-48 NotImplementedError on CPU."""
+    from sstem_restoration_b200 import SeparableConvolution, FunctionSepconv, ModuleSepconv
+    inp = torch.zeros(1, 3, 60, 60)
+    v = torch.zeros(1, 51, 10, 10)
+    with pytest.raises(NotImplementedError):
+        SeparableConvolution.apply(inp, v, v)
+    with pytest.raises(AssertionError):
+        SeparableConvolution.apply(torch.zeros(1, 3, 61, 60), v, v)        # height mismatch
+    with pytest.raises(AssertionError):
+        SeparableConvolution.apply(torch.zeros(1, 3, 58, 58), torch.zeros(1, 49, 10, 10), torch.zeros(1, 49, 10, 10))  # K != 51
+    with pytest.raises(AssertionError):
+        SeparableConvolution.apply(inp.transpose(2, 3), v, v) if False else SeparableConvolution.apply(inp[:, :, :, ::1].permute(0, 1, 3, 2), v, v)
+    # generic-K variant accepts 49 taps but still refuses CPU tensors
+    with pytest.raises(NotImplementedError):
+        FunctionSepconv(torch.zeros(1, 3, 58, 58), torch.zeros(1, 49, 10, 10), torch.zeros(1, 49, 10, 10))
+    with pytest.raises(NotImplementedError):
+        ModuleSepconv()(torch.zeros(1, 3, 58, 58), torch.zeros(1, 49, 10, 10), torch.zeros(1, 49, 10, 10))
+
+
+def test_compat_import_paths(built_lib):
+    """The reference's dotted import paths resolve to the sm_100a implementation."""
+    compat = os.path.join(ROOT, "sstem_restoration_b200", "compat")
+    sys.path.insert(0, compat)
+    try:
+        for m in [k for k in sys.modules if k == "libs" or k.startswith("libs.") or k == "utils" or k.startswith("utils.") or k == "model" or k.startswith("model.")]:
+            del sys.modules[m]
+        from libs.sepconv.SeparableConvolution import SeparableConvolution as S1
+        import sstem_restoration_b200 as pkg
+        assert S1 is pkg.SeparableConvolution
+        import importlib.util
+        for rel, attr in (("utils/image_warp_torch.py", "SpatialTransformation"), ("utils/image_warp.py", "image_warp"),
+                          ("model/sepconv.py", "FunctionSepconv")):
+            spec = importlib.util.spec_from_file_location("compat_" + attr, os.path.join(compat, rel))
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            assert getattr(mod, attr) is getattr(pkg, attr) or getattr(mod, attr) is getattr(pkg.sepconv, attr, None)
+    finally:
+        sys.path.remove(compat)
+
+
+def test_warp_refuses_to_run_without_cuda(built_lib):
+    from sstem_restoration_b200 import SpatialTransformation, image_warp, SstemError
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(SstemError):
+        SpatialTransformation()(torch.zeros(1, 1, 4, 4), torch.zeros(1, 4, 4, 2))
+    with pytest.raises(SstemError):
+        image_warp(np.zeros((4, 4), np.uint8), np.zeros((4, 4, 2), np.float32))
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from sstem_restoration_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.SstemError):
+        _lib.load()
+
+
+def test_shard_ranges_partition_units():
+    from sstem_restoration_b200 import shard
+    for n in (0, 1, 7, 98, 100):
+        for ws in (1, 2, 4, 8):
+            spans = [shard.shard_range(n, r, ws) for r in range(ws)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1 and max(sizes) == shard.max_units_per_rank(n, ws)
+    assert shard.stack_targets(100)[0] == (0, 1, 2) and len(shard.stack_targets(100)) == 98
+    with pytest.raises(ValueError):
+        shard.shard_range(4, 2, 2)
+
+
+def test_synth_inputs_are_deterministic_and_shaped():
+    from sstem_restoration_b200 import synth
+    a, b = synth.em_section(96, 80, 3), synth.em_section(96, 80, 3)
+    assert a.dtype == np.uint8 and a.shape == (96, 80) and np.array_equal(a, b)
+    assert not np.array_equal(a, synth.em_section(96, 80, 4))
+    x = synth.section_to_input(a)
+    assert x.shape == (3, 146, 130) and x.dtype == np.float32 and np.array_equal(x[0], x[2])
+    assert np.array_equal(x[0, 25:-25, 25:-25], a.astype(np.float32) / np.float32(255))
+    t = synth.unit_taps(2, 51, 8, 8)
+    assert t.shape == (2, 51, 8, 8) and np.allclose(t.sum(1), 1, atol=1e-5)
+    f, m = synth.random_fold_flow(128, 128)
+    assert f.shape == (128, 128, 2) and f.dtype == np.float32 and set(np.unique(m)) <= {0.0, 1.0}

@@ -1,0 +1,275 @@
+"""GPU parity tests for the sepconv path.  Everything goes through the C ABI (via the
+reference-shaped autograd Function); the oracle is only the checker.
+
+Tolerances:
+  P0  CPU oracle (reference order) vs the reference's own .cu on the B200: bit-equal.
+  P1  unit-scale inputs (|out| <~ 1): max-abs <= 1e-5 vs the reference-order oracle.
+  P2  raw N(0,1) taps (|out| up to ~1e2): max-abs <= 1e-5 * max(1, max|ref|) AND the
+      kernel's error vs fp64 does not exceed the reference order's own error.
+  STRICT_ORDER flag: bit-equal to the reference order.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from tests import _ref_cuda
+from tests.golden import cases
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+def _cuda(*arrs):
+    return tuple(torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in arrs)
+
+
+def _ops():
+    import sstem_restoration_b200 as pkg
+    return pkg
+
+
+def _fwd(inp, v, h, strict=False):
+    pkg = _ops()
+    pkg.set_strict_order(strict)
+    try:
+        return pkg.SeparableConvolution.apply(inp, v, h)
+    finally:
+        pkg.set_strict_order(False)
+
+
+def _bwd(inp, v, h, g, need_input=True):
+    pkg = _ops()
+    inp = inp.clone().requires_grad_(need_input)
+    v = v.clone().requires_grad_(True)
+    h = h.clone().requires_grad_(True)
+    out = pkg.SeparableConvolution.apply(inp, v, h)
+    out.backward(g)
+    return out.detach(), inp.grad, v.grad, h.grad
+
+
+def _check_p(got, ref32, ref64, what):
+    scale = max(1.0, float(np.abs(ref64).max()))
+    err_vs_ref = float(np.abs(got.astype(np.float64) - ref32).max())
+    err_new = float(np.abs(got - ref64).max())
+    err_ref = float(np.abs(ref32 - ref64).max())
+    assert err_vs_ref <= TOL * scale, f"{what}: |new-ref|={err_vs_ref:.3e} scale={scale:.3g}"
+    assert err_new <= max(err_ref * 1.25, 2e-6 * scale), f"{what}: err(new,f64)={err_new:.3e} > err(ref,f64)={err_ref:.3e}"
+
+
+# ---------------------------------------------------------------- P0: pin the oracle
+@pytest.mark.skipif(not _ref_cuda.available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("name", [n for n, p in cases.sepconv_cases().items() if p["C"] == 3])
+def test_p0_oracle_equals_reference_cuda(name):
+    inp, v, h, g = cases.sepconv_inputs(**cases.sepconv_cases()[name])
+    ti, tv, th, tg = _cuda(inp, v, h, g)
+    out = _ref_cuda.forward(ti, tv, th).cpu().numpy()
+    gi, gv, gh = (t.cpu().numpy() for t in _ref_cuda.backward(tg, ti, tv, th))
+    assert np.array_equal(out.view(np.uint32), oracle.sepconv_forward_reforder(inp, v, h).view(np.uint32))
+    assert np.array_equal(gv.view(np.uint32), oracle.sepconv_grad_vertical_reforder(g, inp, h).view(np.uint32))
+    assert np.array_equal(gh.view(np.uint32), oracle.sepconv_grad_horizontal_reforder(g, inp, v).view(np.uint32))
+    assert not gi.any()   # SeparableConvolution.py:60 -- the reference never computes it
+
+
+def test_golden_fixture_matches_kernel_strict(golden_dir):
+    path = os.path.join(golden_dir, "sepconv_ref.npz")
+    if not os.path.exists(path):
+        pytest.skip("sepconv_ref.npz not committed yet")
+    ref = np.load(path)
+    for name, p in cases.sepconv_cases().items():
+        if p["C"] != 3:
+            continue
+        inp, v, h, g = cases.sepconv_inputs(**p)
+        got = _fwd(*_cuda(inp, v, h), strict=True).cpu().numpy()
+        assert np.array_equal(got.view(np.uint32), ref[name + "_out"].view(np.uint32)), name
+
+
+# ---------------------------------------------------------------- forward
+@pytest.mark.parametrize("name", list(cases.sepconv_cases()))
+def test_forward_strict_order_is_bit_exact(name):
+    inp, v, h, g = cases.sepconv_inputs(**cases.sepconv_cases()[name])
+    got = _fwd(*_cuda(inp, v, h), strict=True).cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), oracle.sepconv_forward_reforder(inp, v, h).view(np.uint32))
+
+
+@pytest.mark.parametrize("name", list(cases.sepconv_cases()))
+def test_forward_parity(name):
+    inp, v, h, g = cases.sepconv_inputs(**cases.sepconv_cases()[name])
+    got = _fwd(*_cuda(inp, v, h)).cpu().numpy()
+    _check_p(got, oracle.sepconv_forward_reforder(inp, v, h), oracle.sepconv_forward_f64(inp, v, h), "fwd " + name)
+
+
+@pytest.mark.parametrize("B,C,H,W", [(1, 3, 1, 1), (1, 1, 1, 70), (1, 3, 70, 1), (2, 2, 33, 65), (1, 4, 8, 129),
+                                      (3, 3, 17, 31), (1, 3, 64, 64), (1, 1, 40, 200), (1, 5, 9, 9)])
+def test_forward_ragged_shapes(B, C, H, W):
+    inp, v, h, g = cases.sepconv_inputs(B, C, H, W, seed=1000 + H * W + C, kind="unit")
+    got = _fwd(*_cuda(inp, v, h)).cpu().numpy()
+    _check_p(got, oracle.sepconv_forward_reforder(inp, v, h), oracle.sepconv_forward_f64(inp, v, h), f"fwd {B,C,H,W}")
+
+
+# ---------------------------------------------------------------- backward
+@pytest.mark.parametrize("name", list(cases.sepconv_cases()))
+def test_backward_parity(name):
+    p = cases.sepconv_cases()[name]
+    inp, v, h, g = cases.sepconv_inputs(**p)
+    out, gi, gv, gh = _bwd(*_cuda(inp, v, h, g))
+    gv64, gh64 = oracle.sepconv_grad_taps_f64(g, inp, v, h)
+    _check_p(gv.cpu().numpy(), oracle.sepconv_grad_vertical_reforder(g, inp, h), gv64, "gv " + name)
+    _check_p(gh.cpu().numpy(), oracle.sepconv_grad_horizontal_reforder(g, inp, v), gh64, "gh " + name)
+    gi64 = oracle.sepconv_grad_input_f64(g, v, h)
+    scale = max(1.0, float(np.abs(gi64).max()))
+    assert np.abs(gi.cpu().numpy() - gi64).max() <= TOL * scale, "gi " + name
+
+
+@pytest.mark.parametrize("B,C,H,W", [(1, 3, 1, 1), (1, 1, 5, 70), (2, 2, 33, 37), (1, 4, 8, 66), (1, 3, 64, 64), (2, 3, 19, 130)])
+def test_backward_ragged_shapes(B, C, H, W):
+    inp, v, h, g = cases.sepconv_inputs(B, C, H, W, seed=2000 + H * W + C, kind="unit")
+    out, gi, gv, gh = _bwd(*_cuda(inp, v, h, g))
+    gv64, gh64 = oracle.sepconv_grad_taps_f64(g, inp, v, h)
+    _check_p(gv.cpu().numpy(), oracle.sepconv_grad_vertical_reforder(g, inp, h), gv64, f"gv {B,C,H,W}")
+    _check_p(gh.cpu().numpy(), oracle.sepconv_grad_horizontal_reforder(g, inp, v), gh64, f"gh {B,C,H,W}")
+    gi64 = oracle.sepconv_grad_input_f64(g, v, h)
+    assert np.abs(gi.cpu().numpy() - gi64).max() <= TOL * max(1.0, float(np.abs(gi64).max()))
+
+
+def test_needs_input_grad_is_honoured():
+    inp, v, h, g = _cuda(*cases.sepconv_inputs(1, 3, 8, 8, seed=5, kind="unit"))
+    out, gi, gv, gh = _bwd(inp, v, h, g, need_input=False)
+    assert gi is None and gv is not None and gh is not None
+    pkg = _ops()
+    v2 = v.clone().requires_grad_(True)
+    pkg.SeparableConvolution.apply(inp, v2, h).backward(g)
+    assert torch.equal(v2.grad, gv)
+
+
+def test_reference_gradcheck_recipe():
+    """sff_scripts_interp/model/model_interp.py:109-119: randn(2,3,51,51), taps (2,51,1,1), eps=atol=rtol=1e-2."""
+    torch.manual_seed(0)
+    pkg = _ops()
+    inputs = (torch.randn(2, 3, 51, 51, device="cuda"),
+              torch.randn(2, 51, 1, 1, device="cuda", requires_grad=True),
+              torch.randn(2, 51, 1, 1, device="cuda", requires_grad=True))
+    assert torch.autograd.gradcheck(pkg.SeparableConvolution.apply, inputs, eps=1e-2, atol=1e-2, rtol=1e-2,
+                                    nondet_tol=0.0, check_grad_dtypes=False)
+
+
+def test_gradcheck_including_input():
+    torch.manual_seed(1)
+    pkg = _ops()
+    inputs = (torch.randn(1, 2, 53, 52, device="cuda", requires_grad=True),
+              torch.randn(1, 51, 3, 2, device="cuda", requires_grad=True),
+              torch.randn(1, 51, 3, 2, device="cuda", requires_grad=True))
+    assert torch.autograd.gradcheck(pkg.SeparableConvolution.apply, inputs, eps=1e-2, atol=2e-2, rtol=2e-2,
+                                    check_grad_dtypes=False)
+
+
+# ---------------------------------------------------------------- generic tap counts (CuPy-variant surface)
+@pytest.mark.parametrize("K", [1, 5, 13, 33, 64])
+def test_function_sepconv_generic_taps(K):
+    pkg = _ops()
+    r = np.random.default_rng(K)
+    B, C, H, W = 2, 3, 11, 14
+    inp = r.standard_normal((B, C, H + K - 1, W + K - 1)).astype(np.float32)
+    v = (r.standard_normal((B, K, H, W)) / K).astype(np.float32)
+    h = (r.standard_normal((B, K, H, W))).astype(np.float32)
+    g = r.standard_normal((B, C, H, W)).astype(np.float32)
+    ti, tv, th, tg = _cuda(inp, v, h, g)
+    ti.requires_grad_(True); tv.requires_grad_(True); th.requires_grad_(True)
+    out = pkg.FunctionSepconv(ti, tv, th)
+    out.backward(tg)
+    ref64 = oracle.sepconv_forward_f64(inp, v, h)
+    assert np.abs(out.detach().cpu().numpy() - ref64).max() <= TOL * max(1.0, np.abs(ref64).max())
+    gv64, gh64 = oracle.sepconv_grad_taps_f64(g, inp, v, h)
+    gi64 = oracle.sepconv_grad_input_f64(g, v, h)
+    for got, ref in ((tv.grad, gv64), (th.grad, gh64), (ti.grad, gi64)):
+        assert np.abs(got.cpu().numpy() - ref).max() <= TOL * max(1.0, np.abs(ref).max())
+    out2 = pkg.ModuleSepconv()(ti.detach(), tv.detach(), th.detach())
+    assert torch.equal(out2, out.detach())
+
+
+# ---------------------------------------------------------------- full-size, size-independent properties
+def _one_hot_taps(B, H, W, seed, device):
+    gen = torch.Generator(device="cpu").manual_seed(seed)
+    fy = torch.randint(0, 51, (B, 1, H, W), generator=gen).to(device)
+    fx = torch.randint(0, 51, (B, 1, H, W), generator=gen).to(device)
+    v = torch.zeros((B, 51, H, W), device=device).scatter_(1, fy, 1.0)
+    h = torch.zeros((B, 51, H, W), device=device).scatter_(1, fx, 1.0)
+    return fy, fx, v, h
+
+
+@pytest.mark.parametrize("B,C,H,W", [(1, 3, 256, 256), (2, 3, 512, 512), (1, 3, 2048, 2048), (1, 1, 1000, 1500)])
+def test_one_hot_taps_select_exact_pixels_at_full_size(B, C, H, W):
+    """With one-hot v and h the op is a pure gather: out[b,c,y,x] = in[b,c,y+fy,x+fx] EXACTLY."""
+    dev = "cuda"
+    torch.manual_seed(3)
+    inp = torch.rand((B, C, H + 50, W + 50), device=dev)
+    fy, fx, v, h = _one_hot_taps(B, H, W, 17, dev)
+    out = _fwd(inp, v, h)
+    yy = torch.arange(H, device=dev).view(1, 1, H, 1) + fy
+    xx = torch.arange(W, device=dev).view(1, 1, 1, W) + fx
+    flat = (yy * (W + 50) + xx).expand(B, C, H, W).reshape(B, C, -1)
+    expect = inp.reshape(B, C, -1).gather(2, flat).reshape(B, C, H, W)
+    assert torch.equal(out, expect)
+    del v, h
+    torch.cuda.empty_cache()
+
+
+def test_linearity_and_tap_gradients_at_training_size():
+    """C3-sized slice: linear in the input; with one-hot taps the tap gradients are plain
+    channel sums of g * shifted input (checked against torch within fp32 rounding of a C-term sum)."""
+    dev = "cuda"
+    B, C, H, W = 2, 3, 512, 512
+    torch.manual_seed(4)
+    x1 = torch.rand((B, C, H + 50, W + 50), device=dev)
+    x2 = torch.rand((B, C, H + 50, W + 50), device=dev)
+    v = torch.softmax(torch.randn((B, 51, H, W), device=dev), 1)
+    h = torch.softmax(torch.randn((B, 51, H, W), device=dev), 1)
+    a = 0.5
+    lhs = _fwd(a * x1 + x2, v, h)
+    rhs = a * _fwd(x1, v, h) + _fwd(x2, v, h)
+    assert (lhs - rhs).abs().max().item() <= 1e-5
+    fy, fx, v1, h1 = _one_hot_taps(B, H, W, 23, dev)
+    g = torch.randn((B, C, H, W), device=dev)
+    out, gi, gv, gh = _bwd(x1, v1, h1, g, need_input=False)
+    # gv[b,f,y,x] = sum_c g * in[b,c,y+f,x+fx]
+    for f in (0, 25, 50):
+        yy = torch.arange(H, device=dev).view(1, 1, H, 1) + f
+        xx = torch.arange(W, device=dev).view(1, 1, 1, W) + fx
+        flat = (yy * (W + 50) + xx).expand(B, C, H, W).reshape(B, C, -1)
+        exp_v = (g * x1.reshape(B, C, -1).gather(2, flat).reshape(B, C, H, W)).sum(1)
+        assert (gv[:, f] - exp_v).abs().max().item() <= 1e-5
+        yy = torch.arange(H, device=dev).view(1, 1, H, 1) + fy
+        xx = torch.arange(W, device=dev).view(1, 1, 1, W) + f
+        flat = (yy * (W + 50) + xx).expand(B, C, H, W).reshape(B, C, -1)
+        exp_h = (g * x1.reshape(B, C, -1).gather(2, flat).reshape(B, C, H, W)).sum(1)
+        assert (gh[:, f] - exp_h).abs().max().item() <= 1e-5
+
+
+def test_adjoint_identity_for_grad_input():
+    """<sepconv(x), g> == <x, grad_input(g)>: ties the computed grad_input to the forward at a mid size."""
+    dev = "cuda"
+    B, C, H, W = 1, 3, 96, 160
+    torch.manual_seed(5)
+    x = torch.randn((B, C, H + 50, W + 50), device=dev)
+    v = torch.softmax(torch.randn((B, 51, H, W), device=dev), 1)
+    h = torch.softmax(torch.randn((B, 51, H, W), device=dev), 1)
+    g = torch.randn((B, C, H, W), device=dev)
+    out, gi, gv, gh = _bwd(x, v, h, g)
+    lhs = (out.double() * g.double()).sum().item()
+    rhs = (x.double() * gi.double()).sum().item()
+    assert abs(lhs - rhs) <= 1e-4 * max(1.0, abs(lhs))
+
+
+def test_other_device_stream_and_noncurrent_stream():
+    """Calls are stream-ordered on torch's current stream."""
+    inp, v, h, g = _cuda(*cases.sepconv_inputs(1, 3, 32, 32, seed=9, kind="unit"))
+    ref = _fwd(inp, v, h)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        got = _fwd(inp, v, h)
+    s.synchronize()
+    assert torch.equal(ref, got)

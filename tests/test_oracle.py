@@ -1,0 +1,116 @@
+"""CPU: the oracle against the reference's own outputs (golden fixtures) and against
+independent restatements (fp64, torch autograd)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from tests.golden import cases
+
+
+# ------------------------------------------------------------------ warps vs reference outputs
+def test_image_warp_restatement_matches_reference_bitwise(golden_dir):
+    ref = np.load(os.path.join(golden_dir, "warp_numpy_ref.npz"))
+    for name, (im, flow, mode) in cases.image_warp_cases().items():
+        got = oracle.image_warp_restated(im, flow, mode)
+        assert got.dtype == np.uint8 and got.shape == ref[name].shape, name
+        assert np.array_equal(got, ref[name]), name
+
+
+def test_image_warp_bad_ndim_raises_like_reference():
+    with pytest.raises(AttributeError):
+        oracle.image_warp_restated(np.zeros((2, 2, 2, 2, 2), np.uint8), np.zeros((2, 2, 2), np.float32))
+
+
+def test_warp_torch_restatement_matches_reference_bitwise(golden_dir):
+    ref = np.load(os.path.join(golden_dir, "warp_torch_ref.npz"))
+    for name, (moving, flow) in cases.warp_torch_cases().items():
+        got = oracle.warp_torch_restated(moving, flow)
+        assert got.shape == ref[name].shape, name
+        assert np.array_equal(got.view(np.uint32), ref[name].view(np.uint32)), name
+
+
+def test_gen_flow_restatement_matches_reference_bitwise(golden_dir):
+    from sstem_restoration_b200 import synth
+    ref = np.load(os.path.join(golden_dir, "gen_flow_ref.npz"))
+    for name, (h, w, p1, p2, lw, fw, dk) in cases.gen_flow_cases().items():
+        k, b = synth.gen_line(p1, p2)
+        assert np.array_equal(np.array([k, b]), ref[name + "_kb"]), name
+        flow, mask = synth.gen_flow(h, w, k, b, lw, fw, dk)
+        assert flow.dtype == np.float32
+        assert np.array_equal(flow.view(np.uint32), ref[name + "_flow"].view(np.uint32)), name
+        assert np.array_equal(mask.astype(np.uint8), ref[name + "_mask"]), name
+
+
+# ------------------------------------------------------------------ sepconv oracle
+def _torch_sepconv_f64(inp, v, h):
+    """Independent shift-and-add restatement in fp64 (torch, differentiable)."""
+    K, H, W = v.shape[1], v.shape[2], v.shape[3]
+    out = 0
+    for fy in range(K):
+        r = 0
+        for fx in range(K):
+            r = r + inp[:, :, fy:fy + H, fx:fx + W] * h[:, fx].unsqueeze(1)
+        out = out + r * v[:, fy].unsqueeze(1)
+    return out
+
+
+@pytest.mark.parametrize("name", list(cases.sepconv_cases()))
+def test_sepconv_oracles_agree(name):
+    p = cases.sepconv_cases()[name]
+    inp, v, h, g = cases.sepconv_inputs(**p)
+    ref32 = oracle.sepconv_forward_reforder(inp, v, h)
+    ref64 = oracle.sepconv_forward_f64(inp, v, h)
+    t = _torch_sepconv_f64(*(torch.from_numpy(a).double() for a in (inp, v, h))).numpy()
+    assert np.allclose(ref64, t, rtol=1e-12, atol=1e-12)
+    scale = max(1.0, np.abs(ref64).max())
+    assert np.abs(ref32 - ref64).max() <= 2e-5 * scale * (50 if p["kind"] == "randn" else 1)
+    fast = oracle.sepconv_fwd_bwd_fast(inp, v, h)
+    assert np.abs(fast - ref64).max() <= 2e-5 * scale * (50 if p["kind"] == "randn" else 1)
+
+
+@pytest.mark.parametrize("name", list(cases.sepconv_cases()))
+def test_sepconv_gradient_oracles_match_autograd(name):
+    p = cases.sepconv_cases()[name]
+    inp, v, h, g = cases.sepconv_inputs(**p)
+    ti, tv, th = (torch.from_numpy(a).double().requires_grad_(True) for a in (inp, v, h))
+    out = _torch_sepconv_f64(ti, tv, th)
+    out.backward(torch.from_numpy(g).double())
+    gv64, gh64 = oracle.sepconv_grad_taps_f64(g, inp, v, h)
+    gi64 = oracle.sepconv_grad_input_f64(g, v, h)
+    assert np.allclose(gv64, tv.grad.numpy(), rtol=1e-11, atol=1e-11)
+    assert np.allclose(gh64, th.grad.numpy(), rtol=1e-11, atol=1e-11)
+    assert np.allclose(gi64, ti.grad.numpy(), rtol=1e-11, atol=1e-11)
+    gv32 = oracle.sepconv_grad_vertical_reforder(g, inp, h)
+    gh32 = oracle.sepconv_grad_horizontal_reforder(g, inp, v)
+    sv, sh = max(1.0, np.abs(gv64).max()), max(1.0, np.abs(gh64).max())
+    assert np.abs(gv32 - gv64).max() <= 1e-4 * sv
+    assert np.abs(gh32 - gh64).max() <= 1e-4 * sh
+    _, gvf, ghf = oracle.sepconv_fwd_bwd_fast(inp, v, h, g)
+    assert np.abs(gvf - gv64).max() <= 1e-4 * sv
+    assert np.abs(ghf - gh64).max() <= 1e-4 * sh
+
+
+def test_sepconv_unfold_torch_baseline_matches_oracle():
+    p = cases.sepconv_cases()["b1c3_16x16_unit"]
+    inp, v, h, g = cases.sepconv_inputs(**p)
+    got = oracle.sepconv_unfold_torch(torch.from_numpy(inp), torch.from_numpy(v), torch.from_numpy(h)).numpy()
+    assert np.abs(got - oracle.sepconv_forward_f64(inp, v, h)).max() <= 1e-5
+
+
+def test_sepconv_oracle_matches_reference_cuda_outputs(golden_dir):
+    """Pin: the reference's own .cu (compiled verbatim, run on a B200) vs the CPU restatement."""
+    path = os.path.join(golden_dir, "sepconv_ref.npz")
+    if not os.path.exists(path):
+        pytest.skip("sepconv_ref.npz not generated yet (needs one GPU run of make_sepconv_ref_golden.py)")
+    ref = np.load(path)
+    for name, p in cases.sepconv_cases().items():
+        if p["C"] != 3:
+            continue
+        inp, v, h, g = cases.sepconv_inputs(**p)
+        assert np.array_equal(oracle.sepconv_forward_reforder(inp, v, h).view(np.uint32), ref[name + "_out"].view(np.uint32)), name
+        assert np.array_equal(oracle.sepconv_grad_vertical_reforder(g, inp, h).view(np.uint32), ref[name + "_gv"].view(np.uint32)), name
+        assert np.array_equal(oracle.sepconv_grad_horizontal_reforder(g, inp, v).view(np.uint32), ref[name + "_gh"].view(np.uint32)), name
+        assert not ref[name + "_gi"].any(), "the reference leaves grad_input zero"

@@ -1,0 +1,58 @@
+"""CPU, world_size 2 over gloo: the N>1 host path (shard -> local work -> gather)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_units, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sstem_restoration_b200 import shard
+    lo, hi = shard.shard_range(n_units, rank, world)
+    # a "restored section" for unit k is a constant plane of value k
+    local = torch.stack([torch.full((2, 3), float(k)) for k in range(lo, hi)]) if hi > lo else torch.zeros((0, 2, 3))
+    full = shard.gather_sections(local, n_units)
+    ok = full.shape == (n_units, 2, 3) and all(bool((full[k] == k).all()) for k in range(n_units))
+    # timing reduction used by bench.py: max over ranks
+    t = torch.tensor([float(rank + 1)])
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    q.put((rank, ok, float(t)))
+    dist.destroy_process_group()
+
+
+def _run(n_units, world=2):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_units, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    return sorted(res)
+
+
+def test_gather_even_split():
+    assert _run(6) == [(0, True, 2.0), (1, True, 2.0)]
+
+
+def test_gather_ragged_split():
+    assert _run(7) == [(0, True, 2.0), (1, True, 2.0)]
+
+
+def test_gather_fewer_units_than_ranks():
+    assert _run(1) == [(0, True, 2.0), (1, True, 2.0)]
