@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path of ssTEM-restoration on B200: sepconv 51-tap fwd+bwd Mpix/s
+(and the flow warp in GB/s) against the kernel rooflines, with the CPU path timed beside it.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
+    python bench.py --impl reference --gpus N --steps K ...  # the CPU baseline arm
+
+One "step" (default workload `c3_train_step`) is the sepconv work of ONE SFF interpolation
+training step (BASELINE.json configs[2]; sff_scripts_interp/model/model_interp.py:94 and its
+backward): two `SeparableConvolution.apply` calls on `in[16,3,562,562]`, `v,h[16,51,512,512]`,
+each followed by its backward for grad_vertical / grad_horizontal (the input does not require
+grad, exactly as in the reference's training loop).  One pixel = one output location of one
+section (all channels): 2 x 16 x 512 x 512 = 8 388 608 pixels per step per GPU.
+
+Prints ONE JSON line (rank 0).  `value` = device-resident throughput (CUDA events, max over
+ranks); `e2e` = the same step through the public operator with HOST (pinned) buffers, H2D of
+input/taps/upstream-grad and D2H of output and both tap gradients inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+K = 51
+FLOP_FWD = lambda C: 2 * C * K * (K + 1)            # noqa: E731  SURVEY.md 8(d): 5304*C per pixel
+FLOP_BWD_TAPS = lambda C: 2 * (C + 2) * K * K       # noqa: E731  26 010 at C = 3
+BYTES_WARP = lambda C: 8 + 8 * C                    # noqa: E731  flow + image read + write per pixel
+
+METRIC = "sepconv_51tap_fwd_bwd_mpix_per_s"
+UNIT = "Mpix/s"
+
+
+# --------------------------------------------------------------------------------------- helpers
+def _dist_env():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        rows = [l for (t, l) in self.lines if t0 <= t <= t1 + 0.3] or [l for (_, l) in self.lines]
+        for l in rows:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path)), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+# --------------------------------------------------------------------------------------- CPU baseline
+def cpu_sepconv_sample(steps: int, warmup: int, threads: int | None = None):
+    """The CPU path BASELINE.json names for sepconv: unfold-based torch-CPU evaluation of
+    kernel.cu:45-49, fwd + autograd bwd for grad_v / grad_h, all host threads; one step =
+    in[1,3,306,306] (a 256x256 section).  Returns (Mpix/s, seconds per step, description)."""
+    import numpy as np
+    import torch
+    import oracle
+    from sstem_restoration_b200 import synth
+
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    H = W = 256
+    inp = torch.from_numpy(synth.section_to_input(synth.em_section(H, W, 0))[None])
+    v = torch.from_numpy(synth.unit_taps(1, K, H, W, seed=1)).requires_grad_(True)
+    h = torch.from_numpy(synth.unit_taps(1, K, H, W, seed=2)).requires_grad_(True)
+    g = torch.from_numpy(np.random.default_rng(99).standard_normal((1, 3, H, W)).astype(np.float32))
+
+    def step():
+        v.grad = None
+        h.grad = None
+        out = oracle.sepconv_unfold_torch(inp, v, h)
+        out.backward(g)
+        return out
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return H * W / dt / 1e6, dt, f"unfold torch-CPU fwd+bwd(gv,gh) of in[1,3,306,306], v,h[1,51,256,256], {steps} steps"
+
+
+def run_reference_arm(args):
+    rank, _, world = _dist_env()
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 20))
+    warm = max(1, min(args.warmup, 3))
+    cores = os.cpu_count() or 1
+    val, dt, sample = cpu_sepconv_sample(steps, warm, cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(val, 4), "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "c3_train_step (bounded CPU sample: one 256x256 section per step; linear in pixels)",
+                   "note": "the reference's sepconv is GPU-only (libs/sepconv/SeparableConvolution.py:47-48); per BASELINE.json "
+                           "the CPU arm is an unfold-based torch-CPU evaluation of the same filter on all host cores"},
+        "cpu_baseline": {"value": round(val, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": round(val, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------- GPU arm
+def run_gpu_arm(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import sstem_restoration_b200 as pkg
+    from sstem_restoration_b200 import shard, synth
+
+    rank, local_rank, world = _dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    sep = pkg.SeparableConvolution.apply
+
+    B, C, H, W = args.batch, 3, args.size, args.size
+    calls = 2                                           # model_interp.py:94: two sepconv calls per step
+    pix_per_step = calls * B * H * W
+
+    # ---- synthetic EM-like inputs, resident in HBM before the timed region ------------------
+    gen = torch.Generator(device=dev).manual_seed(4321 + rank)
+    sets = []
+    for k in range(calls):
+        secs = np.stack([synth.section_to_input(synth.em_section(H, W, 100 * rank + 16 * k + b)) for b in range(B)])
+        inp = torch.from_numpy(secs).to(dev)
+        v = torch.softmax(torch.randn((B, K, H, W), device=dev, generator=gen), 1).requires_grad_(True)
+        h = torch.softmax(torch.randn((B, K, H, W), device=dev, generator=gen), 1).requires_grad_(True)
+        g = torch.randn((B, C, H, W), device=dev, generator=gen)
+        sets.append((inp, v, h, g))
+    ev = lambda: torch.cuda.Event(enable_timing=True)   # noqa: E731
+    kern_events = []
+
+    def step(record=False):
+        outs = []
+        for (inp, v, h, g) in sets:
+            v.grad = None
+            h.grad = None
+            if record:
+                e0, e1, e2 = ev(), ev(), ev()
+                e0.record()
+            out = sep(inp, v, h)
+            if record:
+                e1.record()
+            out.backward(g)
+            if record:
+                e2.record()
+                kern_events.append((e0, e1, e2))
+            outs.append(out.detach())
+        if world > 1:                                   # the path's only exchange: gather the outputs
+            shard.gather_sections(torch.cat(outs, 0), world * calls * B)
+        return outs
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    n0 = pkg.launch_count()
+    t_start, t_stop = ev(), ev()
+    barrier()
+    w0 = time.time()
+    t_start.record()
+    for _ in range(args.steps):
+        step(record=True)
+    t_stop.record()
+    barrier()
+    w1 = time.time()
+    launches = pkg.launch_count() - n0
+    ms_total = t_start.elapsed_time(t_stop)
+    clocks = sampler.stop(w0, w1) if rank == 0 else None
+    tmax = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    lsum = torch.tensor([launches], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lsum, op=dist.ReduceOp.SUM)
+    ms_total = float(tmax.item())
+    ms_step = ms_total / args.steps
+    value = world * pix_per_step / (ms_step * 1e-3) / 1e6
+
+    fwd_ms = statistics.mean(e0.elapsed_time(e1) for e0, e1, _ in kern_events)
+    bwd_ms = statistics.mean(e1.elapsed_time(e2) for _, e1, e2 in kern_events)
+
+    # ---- e2e: same step through the public operator with HOST buffers -----------------------
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, pkg, dev, sets, calls, B, C, H, W, world, dist if world > 1 else None)
+
+    # ---- warp (config 4) on the same device, reported beside the headline -------------------
+    warp = run_warp(args, pkg, dev) if not args.no_warp else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks, peak_src = _peaks()
+    fp32_peak, probe_mhz = pkg.fp32_peak_probe()
+    px_call = B * H * W
+    fwd_tflops = FLOP_FWD(C) * px_call / (fwd_ms * 1e-3) / 1e12
+    bwd_tflops = FLOP_BWD_TAPS(C) * px_call / (bwd_ms * 1e-3) / 1e12
+    rooflines = {
+        "sepconv_fwd": {"bound": "fp32", "achieved": round(fwd_tflops, 3), "peak": round(fp32_peak, 2), "unit": "TFLOP/s",
+                        "frac": round(fwd_tflops / fp32_peak, 4), "ms_per_launch": round(fwd_ms, 4),
+                        "flop_per_pixel": FLOP_FWD(C), "traffic": None},
+        "sepconv_bwd_taps": {"bound": "fp32", "achieved": round(bwd_tflops, 3), "peak": round(fp32_peak, 2), "unit": "TFLOP/s",
+                             "frac": round(bwd_tflops / fp32_peak, 4), "ms_per_launch": round(bwd_ms, 4),
+                             "flop_per_pixel": FLOP_BWD_TAPS(C), "traffic": None},
+    }
+    if warp:
+        hbm = float(peaks.get("hbm_gbs", 6650.0))
+        rooflines["warp"] = {"bound": "hbm", "achieved": round(warp["gbs"], 1), "peak": hbm, "unit": "GB/s",
+                             "frac": round(warp["gbs"] / hbm, 4), "ms_per_launch": round(warp["ms"], 5),
+                             "bytes_per_pixel": BYTES_WARP(3), "traffic": None, "peak_source": peak_src}
+    dominant = "sepconv_bwd_taps" if bwd_ms >= fwd_ms else "sepconv_fwd"
+    roof = dict(rooflines[dominant])
+    roof["kernel"] = dominant
+    roof["peak_source"] = (f"FFMA probe on this GPU in this run (sstem_fp32_peak_probe, {probe_mhz:.0f} MHz seen); nominal "
+                           "148 SM x 128 lanes x 2 x 1.965 GHz = 74.4 TFLOP/s; MEASURED_PEAKS.json has no fp32 row")
+
+    cpu_val, cpu_dt, cpu_sample = cpu_sepconv_sample(steps=3, warmup=1)
+    line = {
+        "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "c3_train_step", "calls_per_step": calls, "input": [B, C, H + 50, W + 50],
+                   "taps": [B, K, H, W], "pixels_per_step_per_gpu": pix_per_step, "parallelism": f"dp{world} (batch shards, no data-path collective; outputs gathered)",
+                   "l2": "working set 7 GB per step >> 126 MB L2 (no flush needed)"},
+        "roofline": roof, "rooflines": rooflines,
+        "cpu_baseline": {"value": round(cpu_val, 4), "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": cpu_sample},
+        "e2e": e2e, "gpu_launches": int(lsum.item()), "clocks": clocks,
+        "extra": {"fwd_mpix_per_s": round(px_call / (fwd_ms * 1e-3) / 1e6, 1), "bwd_taps_mpix_per_s": round(px_call / (bwd_ms * 1e-3) / 1e6, 1),
+                  "warp": warp},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, pkg, dev, sets, calls, B, C, H, W, world, dist):
+    """Host (pinned) buffers in, host buffers out, through SeparableConvolution.apply."""
+    import torch
+    sep = pkg.SeparableConvolution.apply
+    host_in = [tuple(t.detach().cpu().pin_memory() for t in s) for s in sets]
+    host_out = [(torch.empty((B, C, H, W)).pin_memory(), torch.empty((B, K, H, W)).pin_memory(), torch.empty((B, K, H, W)).pin_memory())
+                for _ in sets]
+    h2d = sum(t.numel() * 4 for s in host_in for t in s)
+    d2h = sum(t.numel() * 4 for s in host_out for t in s)
+
+    def step():
+        for (hi, hv, hh, hg), (ho, hgv, hgh) in zip(host_in, host_out):
+            inp = hi.to(dev, non_blocking=True)
+            v = hv.to(dev, non_blocking=True).requires_grad_(True)
+            h = hh.to(dev, non_blocking=True).requires_grad_(True)
+            g = hg.to(dev, non_blocking=True)
+            out = sep(inp, v, h)
+            out.backward(g)
+            ho.copy_(out.detach(), non_blocking=True)
+            hgv.copy_(v.grad, non_blocking=True)
+            hgh.copy_(h.grad, non_blocking=True)
+
+    steps = max(2, min(args.steps, 5))
+    step()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    ms = max(e0.elapsed_time(e1), wall * 1e3)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    return {"value": round(world * calls * B * H * W / (ms * 1e-3) / 1e6, 2), "unit": UNIT, "ms_per_step": round(ms, 3),
+            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": steps,
+            "api": "SeparableConvolution.apply + backward on tensors copied from pinned host memory; out, grad_v, grad_h copied back"}
+
+
+def run_warp(args, pkg, dev):
+    """Config 4 warp: im[1,3,2048,2048], planar-strided flow view; rotating buffer sets > L2."""
+    import numpy as np
+    import torch
+    from sstem_restoration_b200 import synth
+    H = W = 2048
+    st = pkg.SpatialTransformation(True)
+    nsets = 6                                          # 6 x 134 MB = 805 MB >> 126 MB L2
+    flow_np, _ = synth.random_fold_flow(H, W, 555)
+    bufs = []
+    for i in range(nsets):
+        im = torch.from_numpy(np.repeat((synth.em_section(H, W, 50 + i).astype(np.float32) / 255.0)[None, None], 3, 1)).to(dev)
+        planar = torch.from_numpy(np.ascontiguousarray(flow_np.transpose(2, 0, 1))[None]).to(dev) + 0.01 * i
+        bufs.append((im, planar.permute(0, 2, 3, 1)))
+    for im, fl in bufs:
+        st(im, fl)
+    torch.cuda.synchronize()
+    reps = 5
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        for im, fl in bufs:
+            st(im, fl)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / (reps * nsets)
+    gbs = BYTES_WARP(3) * H * W / (ms * 1e-3) / 1e9
+    return {"metric": "warp_gb_per_s", "gbs": gbs, "ms": ms, "gpix_per_s": H * W / (ms * 1e-3) / 1e9,
+            "config": "c4 warp: im[1,3,2048,2048], flow planar [1,2,2048,2048] viewed as [1,2048,2048,2], SFF fold flow; 6 rotating buffer sets (805 MB > L2)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-warp", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,78 @@
+"""Quick kernel-level timing of the sepconv / warp entry points (CUDA events, inputs > L2 rotated).
+Usage: python tools/bench_kernels.py [fwd] [bwd] [warp] [gi]"""
+import os
+import sys
+import json
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import sstem_restoration_b200 as pkg  # noqa: E402
+from sstem_restoration_b200 import _lib  # noqa: E402
+
+K = 51
+
+
+def timeit(fn, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def main():
+    what = set(sys.argv[1:]) or {"fwd", "bwd", "warp"}
+    dev = "cuda"
+    lib = _lib.load()
+    peak, mhz = pkg.fp32_peak_probe()
+    print(json.dumps({"fp32_probe_tflops": round(peak, 2), "probe_mhz": round(mhz)}))
+    for (B, C, H, W) in [(1, 3, 256, 256), (1, 1, 256, 256), (16, 3, 512, 512), (1, 3, 2048, 2048), (1, 1, 2048, 2048)]:
+        torch.manual_seed(0)
+        inp = torch.rand((B, C, H + 50, W + 50), device=dev)
+        v = torch.softmax(torch.randn((B, K, H, W), device=dev), 1)
+        h = torch.softmax(torch.randn((B, K, H, W), device=dev), 1)
+        g = torch.randn((B, C, H, W), device=dev)
+        out = torch.empty((B, C, H, W), device=dev)
+        st = torch.cuda.current_stream().cuda_stream
+        px = B * H * W
+        if "fwd" in what:
+            ms = timeit(lambda: lib.sstem_sepconv_forward(inp.data_ptr(), v.data_ptr(), h.data_ptr(), out.data_ptr(), B, C, H, W, K, 0, st))
+            fl = 2 * C * K * (K + 1) * px
+            print(json.dumps({"op": "fwd", "shape": [B, C, H, W], "ms": round(ms, 4), "gpix_s": round(px / ms / 1e6, 3),
+                              "tflops_alg": round(fl / ms / 1e9, 2), "frac_probe": round(fl / ms / 1e9 / peak, 3),
+                              "tap_GBs": round(px * 408 / ms / 1e6, 1)}))
+        if "bwd" in what:
+            gv, gh = torch.empty_like(v), torch.empty_like(h)
+            ms = timeit(lambda: lib.sstem_sepconv_backward(g.data_ptr(), inp.data_ptr(), v.data_ptr(), h.data_ptr(), None, gv.data_ptr(), gh.data_ptr(), B, C, H, W, K, 0, st), reps=3, warm=1)
+            fl = 2 * (C + 2) * K * K * px
+            print(json.dumps({"op": "bwd_taps", "shape": [B, C, H, W], "ms": round(ms, 4), "gpix_s": round(px / ms / 1e6, 3),
+                              "tflops_alg": round(fl / ms / 1e9, 2), "frac_probe": round(fl / ms / 1e9 / peak, 3)}))
+            del gv, gh
+        if "gi" in what and px <= 16 * 512 * 512:
+            gi = torch.empty_like(inp)
+            ms = timeit(lambda: lib.sstem_sepconv_backward(g.data_ptr(), inp.data_ptr(), v.data_ptr(), h.data_ptr(), gi.data_ptr(), None, None, B, C, H, W, K, 0, st), reps=2, warm=1)
+            fl = 2 * C * K * (K + 1) * px
+            print(json.dumps({"op": "bwd_input", "shape": [B, C, H, W], "ms": round(ms, 4), "gpix_s": round(px / ms / 1e6, 3), "tflops_alg": round(fl / ms / 1e9, 2)}))
+        del inp, v, h, g, out
+        torch.cuda.empty_cache()
+    if "warp" in what:
+        st = pkg.SpatialTransformation(True)
+        for (B, C, H, W) in [(1, 3, 2048, 2048), (1, 3, 4096, 4096), (1, 1, 4096, 4096)]:
+            n = max(2, int(1.0e9 // (B * H * W * (8 * C + 8))))
+            sets = [(torch.rand((B, C, H, W), device=dev), (5 * torch.randn((B, 2, H, W), device=dev)).permute(0, 2, 3, 1)) for _ in range(n)]
+            smooth = [(a, (torch.zeros((B, 2, H, W), device=dev) + 3.3).permute(0, 2, 3, 1)) for a, _ in sets]
+            for name, ss in (("noise5px", sets), ("const3.3px", smooth)):
+                ms = timeit(lambda: [st(a, f) for a, f in ss]) / n
+                print(json.dumps({"op": "warp_" + name, "shape": [B, C, H, W], "ms": round(ms, 5), "GBs": round(B * H * W * (8 * C + 8) / ms / 1e6, 1),
+                                  "gpix_s": round(B * H * W / ms / 1e6, 2)}))
+            del sets, smooth
+            torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,39 @@
+"""Runs a few launches of one op for profiling under ncu.  usage: run_one.py <fwd|bwd|gi|warp> B C H W [reps]"""
+import os
+import sys
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import sstem_restoration_b200 as pkg  # noqa: E402
+from sstem_restoration_b200 import _lib  # noqa: E402
+
+op = sys.argv[1]
+B, C, H, W = (int(a) for a in sys.argv[2:6])
+reps = int(sys.argv[6]) if len(sys.argv) > 6 else 3
+K = 51
+dev = "cuda"
+lib = _lib.load()
+torch.manual_seed(0)
+st = torch.cuda.current_stream().cuda_stream
+if op == "warp":
+    im = torch.rand((B, C, H, W), device=dev)
+    fl = (5 * torch.randn((B, 2, H, W), device=dev)).permute(0, 2, 3, 1)
+    m = pkg.SpatialTransformation(True)
+    for _ in range(reps):
+        m(im, fl)
+else:
+    inp = torch.rand((B, C, H + 50, W + 50), device=dev)
+    v = torch.softmax(torch.randn((B, K, H, W), device=dev), 1)
+    h = torch.softmax(torch.randn((B, K, H, W), device=dev), 1)
+    g = torch.randn((B, C, H, W), device=dev)
+    out = torch.empty((B, C, H, W), device=dev)
+    gv, gh, gi = torch.empty_like(v), torch.empty_like(h), torch.empty_like(inp)
+    for _ in range(reps):
+        if op == "fwd":
+            lib.sstem_sepconv_forward(inp.data_ptr(), v.data_ptr(), h.data_ptr(), out.data_ptr(), B, C, H, W, K, 0, st)
+        elif op == "bwd":
+            lib.sstem_sepconv_backward(g.data_ptr(), inp.data_ptr(), v.data_ptr(), h.data_ptr(), None, gv.data_ptr(), gh.data_ptr(), B, C, H, W, K, 0, st)
+        elif op == "gi":
+            lib.sstem_sepconv_backward(g.data_ptr(), inp.data_ptr(), v.data_ptr(), h.data_ptr(), gi.data_ptr(), None, None, B, C, H, W, K, 0, st)
+torch.cuda.synchronize()
+print("done", op, B, C, H, W)
