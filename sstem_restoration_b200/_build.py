@@ -41,6 +41,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB_PATH
     cmd = [_nvcc()] + [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + ["-o", LIB_PATH + ".tmp"]
+    cmd += os.environ.get("SSTEM_NVCC_EXTRA", "").split()        # experiments only, e.g. -DSSTEM_BWD_ROWS=6
     cmd += [os.path.join(CSRC, s) for s in SOURCES]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     log = proc.stdout + proc.stderr
