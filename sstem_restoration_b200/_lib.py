@@ -10,7 +10,10 @@ import ctypes
 import os
 import threading
 
-from ._build import LIB_PATH
+from ._build import LIB_PATH as _DEFAULT_LIB_PATH
+
+#: SSTEM_LIB_PATH selects another build of the same library (kernel-tuning experiments)
+LIB_PATH = os.environ.get("SSTEM_LIB_PATH") or _DEFAULT_LIB_PATH
 
 _c_i64 = ctypes.c_int64
 _c_i32 = ctypes.c_int32

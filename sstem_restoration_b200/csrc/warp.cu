@@ -13,6 +13,8 @@
 // in the reference's operation order, so results are bit-equal to the CPU run of
 // the reference, not merely close.
 #include "common.cuh"
+#include <cuda.h>
+#include <stdlib.h>
 
 namespace sstem {
 
@@ -47,8 +49,16 @@ __device__ __forceinline__ float padded_at(const float* __restrict__ im, int py,
     return ((unsigned)yy < (unsigned)H && (unsigned)xx < (unsigned)W) ? __ldg(im + (int64_t)yy * W + xx) : 0.f;
 }
 
-template <int PX, bool NHWC>
-__global__ void __launch_bounds__(256)
+// CT = compile-time channel count (0 = runtime loop).  With CT > 0 all 4*CT*PX gathers of a
+// thread are independent straight-line loads, so they are in flight together.
+#ifndef SSTEM_WARP_PX
+#define SSTEM_WARP_PX 1
+#endif
+#ifndef SSTEM_WARP_MINB
+#define SSTEM_WARP_MINB 6
+#endif
+template <int PX, bool NHWC, int CT>
+__global__ void __launch_bounds__(256, SSTEM_WARP_MINB)
 warp_torch_kernel(const float* __restrict__ moving, const float* __restrict__ flow,
                   int64_t fs_b, int64_t fs_h, int64_t fs_w, int64_t fs_c,
                   float* __restrict__ out, int C, int H, int W, int groups_per_row, int64_t total_groups) {
@@ -59,8 +69,8 @@ warp_torch_kernel(const float* __restrict__ moving, const float* __restrict__ fl
     const int64_t b = gidx / ((int64_t)groups_per_row * H);
     const int j0 = gx * PX;
     const int64_t plane = (int64_t)H * W;
+    const int nc = CT > 0 ? CT : C;
 
-    BilinearTap tap[PX];
     const float* frow = flow + b * fs_b + (int64_t)i * fs_h;
     const bool full = (j0 + PX <= W);
     // flow: vector loads when the two components are separate contiguous planes
@@ -71,6 +81,10 @@ warp_torch_kernel(const float* __restrict__ moving, const float* __restrict__ fl
         const float4 c = __ldcs(reinterpret_cast<const float4*>(frow + fs_c + j0));
         fxv[0] = a.x; fxv[1 % PX] = a.y; fxv[2 % PX] = a.z; fxv[3 % PX] = a.w;
         fyv[0] = c.x; fyv[1 % PX] = c.y; fyv[2 % PX] = c.z; fyv[3 % PX] = c.w;
+    } else if (PX == 2 && full && fs_w == 1 && (((uintptr_t)(frow + j0) | (uintptr_t)(frow + fs_c + j0)) & 7u) == 0) {
+        const float2 a = __ldcs(reinterpret_cast<const float2*>(frow + j0));
+        const float2 c = __ldcs(reinterpret_cast<const float2*>(frow + fs_c + j0));
+        fxv[0] = a.x; fxv[1 % PX] = a.y; fyv[0] = c.x; fyv[1 % PX] = c.y;
     } else if (PX == 4 && full && fs_w == 2 && fs_c == 1 && ((uintptr_t)(frow + 2 * j0) & 15u) == 0) {
         const float4 a = __ldcs(reinterpret_cast<const float4*>(frow + 2 * j0));
         const float4 c = __ldcs(reinterpret_cast<const float4*>(frow + 2 * j0 + 4));
@@ -84,40 +98,268 @@ warp_torch_kernel(const float* __restrict__ moving, const float* __restrict__ fl
             fyv[p] = __ldg(frow + (int64_t)j * fs_w + fs_c);
         }
     }
+    // per pixel: the 4 source offsets inside a plane (or -1 when the tap lies in the zero border)
+    int oa[PX], ob[PX], oc[PX], od[PX];
+    float wa[PX], wb[PX], wc[PX], wd[PX];
 #pragma unroll
-    for (int p = 0; p < PX; ++p) tap[p] = torch_tap(fxv[p], fyv[p], i, j0 + p, H, W);
-
-    for (int c = 0; c < C; ++c) {
-        const float* im = moving + (b * C + c) * plane;
+    for (int p = 0; p < PX; ++p) {
+        const BilinearTap t = torch_tap(fxv[p], fyv[p], i, j0 + p, H, W);
+        const int xa = t.x0 - 1, xb = t.x1 - 1, ya = t.y0 - 1, yb = t.y1 - 1;
+        const bool vxa = (unsigned)xa < (unsigned)W, vxb = (unsigned)xb < (unsigned)W;
+        const bool vya = (unsigned)ya < (unsigned)H, vyb = (unsigned)yb < (unsigned)H;
+        oa[p] = (vya && vxa) ? ya * W + xa : -1;      // (y0, x0)
+        ob[p] = (vyb && vxa) ? yb * W + xa : -1;      // (y1, x0)
+        oc[p] = (vya && vxb) ? ya * W + xb : -1;      // (y0, x1)
+        od[p] = (vyb && vxb) ? yb * W + xb : -1;      // (y1, x1)
+        wa[p] = t.wa; wb[p] = t.wb; wc[p] = t.wc; wd[p] = t.wd;
+    }
+    auto channel = [&](int c) {
+        const float* im = moving + (b * nc + c) * plane;
+        float Ia[PX], Ib[PX], Ic[PX], Id[PX];
+#pragma unroll
+        for (int p = 0; p < PX; ++p) {
+            Ia[p] = oa[p] >= 0 ? __ldg(im + oa[p]) : 0.f;
+            Ib[p] = ob[p] >= 0 ? __ldg(im + ob[p]) : 0.f;
+            Ic[p] = oc[p] >= 0 ? __ldg(im + oc[p]) : 0.f;
+            Id[p] = od[p] >= 0 ? __ldg(im + od[p]) : 0.f;
+        }
         float res[PX];
 #pragma unroll
         for (int p = 0; p < PX; ++p) {
-            const BilinearTap& t = tap[p];
-            const float Ia = padded_at(im, t.y0, t.x0, H, W);
-            const float Ib = padded_at(im, t.y1, t.x0, H, W);
-            const float Ic = padded_at(im, t.y0, t.x1, H, W);
-            const float Id = padded_at(im, t.y1, t.x1, H, W);
             // image_warp_torch.py:93: sum over the stacked [wa*Ia, wb*Ib, wc*Ic, wd*Id]
-            float r = __fadd_rn(__fmul_rn(t.wa, Ia), __fmul_rn(t.wb, Ib));
-            r = __fadd_rn(r, __fmul_rn(t.wc, Ic));
-            r = __fadd_rn(r, __fmul_rn(t.wd, Id));
+            float r = __fadd_rn(__fmul_rn(wa[p], Ia[p]), __fmul_rn(wb[p], Ib[p]));
+            r = __fadd_rn(r, __fmul_rn(wc[p], Ic[p]));
+            r = __fadd_rn(r, __fmul_rn(wd[p], Id[p]));
             res[p] = r;
         }
         if (NHWC) {
 #pragma unroll
             for (int p = 0; p < PX; ++p)
-                if (j0 + p < W) out[((b * H + i) * (int64_t)W + j0 + p) * C + c] = res[p];
+                if (j0 + p < W) out[((b * H + i) * (int64_t)W + j0 + p) * nc + c] = res[p];
         } else {
-            float* orow = out + (b * C + c) * plane + (int64_t)i * W + j0;
+            float* orow = out + (b * nc + c) * plane + (int64_t)i * W + j0;
             if (PX == 4 && full && ((uintptr_t)orow & 15u) == 0) {
                 __stcs(reinterpret_cast<float4*>(orow), make_float4(res[0], res[1 % PX], res[2 % PX], res[3 % PX]));
+            } else if (PX == 2 && full && ((uintptr_t)orow & 7u) == 0) {
+                __stcs(reinterpret_cast<float2*>(orow), make_float2(res[0], res[1 % PX]));
             } else {
 #pragma unroll
                 for (int p = 0; p < PX; ++p)
                     if (j0 + p < W) orow[p] = res[p];
             }
         }
+    };
+    if (CT > 0) {
+#pragma unroll
+        for (int c = 0; c < CT; ++c) channel(c);
+    } else {
+        for (int c = 0; c < C; ++c) channel(c);
     }
+}
+
+// ---- TMA-tiled variant ------------------------------------------------------------------------
+// A CTA owns a TH x TW output tile.  Thread 0 pulls the tile's two flow planes into shared memory
+// with TMA (cp.async.bulk.tensor, completion on an mbarrier); every thread derives its taps, a
+// redux-based block reduction gives the bounding box of all in-image taps, and when that box fits
+// BH x BW the source window of all channels arrives with ONE more TMA load (out-of-image parts of
+// the box are zero-filled by the hardware = the reference's zero padding); the gathers then hit
+// shared memory.  Tiles whose taps spread further (fold lines, very rough flows) gather from
+// global memory instead.  No registers are tied up by bytes in flight, which is what lets an
+// HBM-bound gather approach copy bandwidth.  Needs W % 4 == 0, planar flow (stride 1 along x) and
+// 16-byte aligned bases (tensor-map rules); otherwise the direct kernel above runs.
+constexpr int WT_TH = 16, WT_TW = 64;      // output tile
+constexpr int WT_BH = 32, WT_BW = 96;      // source window (box of the image tensor map)
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"(a), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(map), "r"((unsigned)__cvta_generic_to_shared(bar)),
+          "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+#ifndef SSTEM_WARP_TMA_MINB
+#define SSTEM_WARP_TMA_MINB 3
+#endif
+template <int CT>
+__global__ void __launch_bounds__(256, SSTEM_WARP_TMA_MINB)
+warp_torch_tma_kernel(const __grid_constant__ CUtensorMap map_fx, const __grid_constant__ CUtensorMap map_fy,
+                      const __grid_constant__ CUtensorMap map_im, const float* __restrict__ moving,
+                      float* __restrict__ out, int H, int W) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* s_im = reinterpret_cast<float*>(smem_raw);                       // [CT][BH][BW]
+    float* s_fx = s_im + CT * WT_BH * WT_BW;                                // [TH][TW]
+    float* s_fy = s_fx + WT_TH * WT_TW;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_fy + WT_TH * WT_TW);      // 2 barriers
+    int* s_box = reinterpret_cast<int*>(bar + 2);                           // min x, min y, max x, max y
+
+    const int tid = threadIdx.x;
+    const int j00 = blockIdx.x * WT_TW, i0 = blockIdx.y * WT_TH;
+    const int b = blockIdx.z;
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        s_box[0] = INT32_MAX; s_box[1] = INT32_MAX; s_box[2] = INT32_MIN; s_box[3] = INT32_MIN;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&bar[0], 2u * WT_TH * WT_TW * sizeof(float));
+        tma_load_3d(s_fx, &map_fx, &bar[0], j00, i0, b);
+        tma_load_3d(s_fy, &map_fy, &bar[0], j00, i0, b);
+    }
+    // thread -> 4 pixels: rows (warp, warp + 8) x columns (lane, lane + 32).  Lanes walk along x,
+    // so shared-memory reads are bank-conflict free and every global store is a full 128-byte line.
+    const int warp = tid >> 5, lane = tid & 31;
+    mbar_wait(&bar[0], 0);
+
+    int offa[4];                                        // (y0, x0) relative to the window origin, filled in below
+    int xa[4], ya[4], dxs[4], dys[4];                   // x0 / y0 in image coordinates (-1 .. W / H); x1-x0, y1-y0
+    float wa[4], wb[4], wc[4], wd[4];
+    int mnx = INT32_MAX, mny = INT32_MAX, mxx = INT32_MIN, mxy = INT32_MIN;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int r = warp + 8 * (q >> 1), cidx = lane + 32 * (q & 1);
+        const int i = i0 + r, j = j00 + cidx;
+        const BilinearTap t = torch_tap(s_fx[r * WT_TW + cidx], s_fy[r * WT_TW + cidx], i, j, H, W);
+        xa[q] = t.x0 - 1; ya[q] = t.y0 - 1;
+        dxs[q] = t.x1 - t.x0; dys[q] = t.y1 - t.y0;
+        wa[q] = t.wa; wb[q] = t.wb; wc[q] = t.wc; wd[q] = t.wd;
+        if (i < H && j < W) {
+            // the window must cover every tap, including those in the zero border (-1 / W / H):
+            // TMA zero-fills whatever lies outside the image, which IS the reference's padding
+            mnx = min(mnx, xa[q]); mxx = max(mxx, xa[q] + dxs[q]);
+            mny = min(mny, ya[q]); mxy = max(mxy, ya[q] + dys[q]);
+        }
+    }
+    mnx = __reduce_min_sync(0xffffffffu, mnx); mny = __reduce_min_sync(0xffffffffu, mny);
+    mxx = __reduce_max_sync(0xffffffffu, mxx); mxy = __reduce_max_sync(0xffffffffu, mxy);
+    if (lane == 0) {
+        atomicMin(&s_box[0], mnx); atomicMin(&s_box[1], mny); atomicMax(&s_box[2], mxx); atomicMax(&s_box[3], mxy);
+    }
+    __syncthreads();
+    // the box must start on a 16-byte boundary in global memory: round the left edge down to 4 floats
+    const int bx0 = s_box[0] & ~3, by0 = s_box[1], bx1 = s_box[2], by1 = s_box[3];
+    const bool fits = (bx1 - bx0 < WT_BW) && (by1 - by0 < WT_BH);
+    if (fits && tid == 0) {
+        mbar_expect_tx(&bar[1], (unsigned)(CT * WT_BH * WT_BW * sizeof(float)));
+        tma_load_3d(s_im, &map_im, &bar[1], bx0, by0, b * CT);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) offa[q] = (ya[q] - by0) * WT_BW + (xa[q] - bx0);
+    const int64_t plane = (int64_t)H * W;
+    float* obase = out + (int64_t)b * CT * plane;
+    if (fits) {
+        mbar_wait(&bar[1], 0);
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float* sp = s_im + c * (WT_BH * WT_BW) + offa[q];
+                const int dy = dys[q] * WT_BW;
+                const float Ia = sp[0], Ib = sp[dy], Ic = sp[dxs[q]], Id = sp[dy + dxs[q]];
+                float r = __fadd_rn(__fmul_rn(wa[q], Ia), __fmul_rn(wb[q], Ib));
+                r = __fadd_rn(r, __fmul_rn(wc[q], Ic));
+                r = __fadd_rn(r, __fmul_rn(wd[q], Id));
+                const int i = i0 + warp + 8 * (q >> 1), j = j00 + lane + 32 * (q & 1);
+                if (i < H && j < W) __stcs(obase + c * plane + (int64_t)i * W + j, r);
+            }
+        }
+    } else {
+        // taps spread beyond the window: gather from global memory (zero outside the image)
+#pragma unroll 1
+        for (int c = 0; c < CT; ++c) {
+            const float* im = moving + ((int64_t)b * CT + c) * plane;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int x0 = xa[q], y0 = ya[q], x1 = x0 + dxs[q], y1 = y0 + dys[q];
+                const bool vx0 = (unsigned)x0 < (unsigned)W, vx1 = (unsigned)x1 < (unsigned)W;
+                const bool vy0 = (unsigned)y0 < (unsigned)H, vy1 = (unsigned)y1 < (unsigned)H;
+                const float Ia = (vy0 && vx0) ? __ldg(im + (int64_t)y0 * W + x0) : 0.f;
+                const float Ib = (vy1 && vx0) ? __ldg(im + (int64_t)y1 * W + x0) : 0.f;
+                const float Ic = (vy0 && vx1) ? __ldg(im + (int64_t)y0 * W + x1) : 0.f;
+                const float Id = (vy1 && vx1) ? __ldg(im + (int64_t)y1 * W + x1) : 0.f;
+                float r = __fadd_rn(__fmul_rn(wa[q], Ia), __fmul_rn(wb[q], Ib));
+                r = __fadd_rn(r, __fmul_rn(wc[q], Ic));
+                r = __fadd_rn(r, __fmul_rn(wd[q], Id));
+                const int i = i0 + warp + 8 * (q >> 1), j = j00 + lane + 32 * (q & 1);
+                if (i < H && j < W) __stcs(obase + c * plane + (int64_t)i * W + j, r);
+            }
+        }
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+// 3-D fp32 tensor map over (x: W, y: H, z: n) with strides (1, row, slab) in elements
+static bool make_map3(CUtensorMap* m, const float* base, int64_t W, int64_t H, int64_t n, int64_t row, int64_t slab,
+                      int bw, int bh, int bn) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
+    const cuuint64_t strides[2] = {(cuuint64_t)row * 4, (cuuint64_t)slab * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// returns 0 on launch, >0 cuda error, -1000 when the TMA path does not apply (caller falls back)
+template <int CT>
+static int try_launch_warp_tma(const float* moving, const float* flow, const int64_t* fs, float* out,
+                               int64_t B, int64_t H, int64_t W, cudaStream_t s) {
+    if ((W & 3) || fs[2] != 1 || !aligned16(moving) || !aligned16(flow) || !aligned16(out)) return -1000;
+    if ((fs[0] & 3) || (fs[1] & 3) || (fs[3] & 3) || fs[1] < W || B > 65535 || (H + WT_TH - 1) / WT_TH > 65535) return -1000;
+    CUtensorMap mfx, mfy, mim;
+    if (!make_map3(&mfx, flow, W, H, B, fs[1], fs[0], WT_TW, WT_TH, 1)) return -1000;
+    if (!make_map3(&mfy, flow + fs[3], W, H, B, fs[1], fs[0], WT_TW, WT_TH, 1)) return -1000;
+    if (!make_map3(&mim, moving, W, H, B * CT, W, H * W, WT_BW, WT_BH, CT)) return -1000;
+    const size_t smem = (size_t)(CT * WT_BH * WT_BW + 2 * WT_TH * WT_TW) * sizeof(float) + 64;
+    static bool done[16] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!done[dev & 15]) {
+        cudaError_t e = cudaFuncSetAttribute(warp_torch_tma_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        done[dev & 15] = true;
+    }
+    dim3 grid((unsigned)((W + WT_TW - 1) / WT_TW), (unsigned)((H + WT_TH - 1) / WT_TH), (unsigned)B);
+    warp_torch_tma_kernel<CT><<<grid, 256, smem, s>>>(mfx, mfy, mim, moving, out, (int)H, (int)W);
+    count_launch();
+    return finish_launch();
 }
 
 // ---- numpy image_warp semantics -------------------------------------------------
@@ -185,16 +427,26 @@ extern "C" int sstem_warp_forward(const float* moving, const float* flow, const 
     DeviceGuard guard(out);
     if (guard.err) return guard.err;
     cudaStream_t s = (cudaStream_t)stream;
-    constexpr int PX = 4;
+    if (H * W > INT32_MAX) return SSTEM_E_SHAPE;       // in-plane offsets are 32-bit
+    static const bool no_tma = getenv("SSTEM_WARP_NO_TMA") != nullptr;   // experiments: force the direct kernel
+    if (out_layout == SSTEM_LAYOUT_NCHW && (C == 1 || C == 3) && !no_tma) {
+        const int r = (C == 3) ? try_launch_warp_tma<3>(moving, flow, flow_strides, out, B, H, W, s)
+                               : try_launch_warp_tma<1>(moving, flow, flow_strides, out, B, H, W, s);
+        if (r != -1000) return r;
+    }
+    constexpr int PX = SSTEM_WARP_PX;
     const int gpr = (int)((W + PX - 1) / PX);
     const int64_t groups = B * H * gpr;
     const unsigned blocks = (unsigned)((groups + 255) / 256);
-    if (out_layout == SSTEM_LAYOUT_NHWC)
-        warp_torch_kernel<PX, true><<<blocks, 256, 0, s>>>(moving, flow, flow_strides[0], flow_strides[1], flow_strides[2],
-                                                           flow_strides[3], out, (int)C, (int)H, (int)W, gpr, groups);
-    else
-        warp_torch_kernel<PX, false><<<blocks, 256, 0, s>>>(moving, flow, flow_strides[0], flow_strides[1], flow_strides[2],
-                                                            flow_strides[3], out, (int)C, (int)H, (int)W, gpr, groups);
+#define SSTEM_WARP_LAUNCH(NHWC_, CT_)                                                                        \
+    warp_torch_kernel<PX, NHWC_, CT_><<<blocks, 256, 0, s>>>(moving, flow, flow_strides[0], flow_strides[1],  \
+                                                             flow_strides[2], flow_strides[3], out, (int)C,   \
+                                                             (int)H, (int)W, gpr, groups)
+    const bool nhwc = out_layout == SSTEM_LAYOUT_NHWC;
+    if (C == 3) { if (nhwc) SSTEM_WARP_LAUNCH(true, 3); else SSTEM_WARP_LAUNCH(false, 3); }
+    else if (C == 1) { if (nhwc) SSTEM_WARP_LAUNCH(true, 1); else SSTEM_WARP_LAUNCH(false, 1); }
+    else { if (nhwc) SSTEM_WARP_LAUNCH(true, 0); else SSTEM_WARP_LAUNCH(false, 0); }
+#undef SSTEM_WARP_LAUNCH
     count_launch();
     return finish_launch();
 }

@@ -17,7 +17,11 @@ torch.manual_seed(0)
 st = torch.cuda.current_stream().cuda_stream
 if op == "warp":
     im = torch.rand((B, C, H, W), device=dev)
-    fl = (5 * torch.randn((B, 2, H, W), device=dev)).permute(0, 2, 3, 1)
+    kind = os.environ.get("FLOW", "noise")
+    if kind == "noise":
+        fl = (5 * torch.randn((B, 2, H, W), device=dev)).permute(0, 2, 3, 1)
+    else:
+        fl = (torch.zeros((B, 2, H, W), device=dev) + 3.3).permute(0, 2, 3, 1)
     m = pkg.SpatialTransformation(True)
     for _ in range(reps):
         m(im, fl)
