@@ -59,7 +59,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -94,6 +94,15 @@ class ClockSampler:
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def _traffic():
+    """DRAM bytes per launch from the committed `ncu --set full` captures (profiles/traffic_r1.json)."""
+    path = os.path.join(ROOT, "profiles", "traffic_r1.json")
+    try:
+        return json.load(open(path))
+    except Exception:
+        return {}
 
 
 def _peaks():
@@ -176,6 +185,8 @@ def run_gpu_arm(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
+            os.environ["NCCL_DEBUG"] = "WARN"            # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     sep = pkg.SeparableConvolution.apply
 
@@ -284,6 +295,13 @@ def run_gpu_arm(args):
         rooflines["warp"] = {"bound": "hbm", "achieved": round(warp["gbs"], 1), "peak": hbm, "unit": "GB/s",
                              "frac": round(warp["gbs"] / hbm, 4), "ms_per_launch": round(warp["ms"], 5),
                              "bytes_per_pixel": BYTES_WARP(3), "traffic": None, "peak_source": peak_src}
+    traffic = _traffic()
+    for name, r in rooflines.items():
+        t = traffic.get(name)
+        if t and (name == "warp" or (B * H * W == t.get("pixels_per_launch"))):
+            r["traffic"] = t["dram_bytes_per_launch"]
+            r["traffic_source"] = t["source"]
+            r["algorithmic_bytes_per_launch"] = t["algorithmic_bytes_per_launch"]
     dominant = "sepconv_bwd_taps" if bwd_ms >= fwd_ms else "sepconv_fwd"
     roof = dict(rooflines[dominant])
     roof["kernel"] = dominant
@@ -310,9 +328,9 @@ def run_gpu_arm(args):
 
 
 def run_e2e(args, pkg, dev, sets, calls, B, C, H, W, world, dist):
-    """Host (pinned) buffers in, host buffers out, through SeparableConvolution.apply."""
+    """Host (pinned) buffers in, host buffers out: the step through the host-buffer entry point
+    (sepconv_forward_backward_host: chunked H2D -> C-ABI kernels -> D2H on rotating streams)."""
     import torch
-    sep = pkg.SeparableConvolution.apply
     host_in = [tuple(t.detach().cpu().pin_memory() for t in s) for s in sets]
     host_out = [(torch.empty((B, C, H, W)).pin_memory(), torch.empty((B, K, H, W)).pin_memory(), torch.empty((B, K, H, W)).pin_memory())
                 for _ in sets]
@@ -320,16 +338,8 @@ def run_e2e(args, pkg, dev, sets, calls, B, C, H, W, world, dist):
     d2h = sum(t.numel() * 4 for s in host_out for t in s)
 
     def step():
-        for (hi, hv, hh, hg), (ho, hgv, hgh) in zip(host_in, host_out):
-            inp = hi.to(dev, non_blocking=True)
-            v = hv.to(dev, non_blocking=True).requires_grad_(True)
-            h = hh.to(dev, non_blocking=True).requires_grad_(True)
-            g = hg.to(dev, non_blocking=True)
-            out = sep(inp, v, h)
-            out.backward(g)
-            ho.copy_(out.detach(), non_blocking=True)
-            hgv.copy_(v.grad, non_blocking=True)
-            hgh.copy_(h.grad, non_blocking=True)
+        for (hi, hv, hh, hg), ho in zip(host_in, host_out):
+            pkg.sepconv_forward_backward_host(hi, hv, hh, hg, device=dev, out=ho)
 
     steps = max(2, min(args.steps, 5))
     step()
@@ -349,9 +359,13 @@ def run_e2e(args, pkg, dev, sets, calls, B, C, H, W, world, dist):
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item()) / steps
+    # spot-check the host path against the device-resident path (same kernels, same inputs)
+    ref = pkg.SeparableConvolution.apply(sets[0][0][:1], sets[0][1][:1].detach(), sets[0][2][:1].detach())
+    same = bool(torch.equal(ref.cpu(), host_out[0][0][:1]))
     return {"value": round(world * calls * B * H * W / (ms * 1e-3) / 1e6, 2), "unit": UNIT, "ms_per_step": round(ms, 3),
-            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": steps,
-            "api": "SeparableConvolution.apply + backward on tensors copied from pinned host memory; out, grad_v, grad_h copied back"}
+            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": steps, "matches_device_path": same,
+            "api": "sepconv_forward_backward_host(pinned input, vertical, horizontal, grad_output) -> pinned output, grad_vertical, "
+                   "grad_horizontal; batch chunks of 2 on 3 streams (H2D, C-ABI fwd+bwd kernels, D2H overlapped)"}
 
 
 def run_warp(args, pkg, dev):
@@ -388,7 +402,7 @@ def run_warp(args, pkg, dev):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=16)

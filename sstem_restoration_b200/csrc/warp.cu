@@ -167,8 +167,17 @@ warp_torch_kernel(const float* __restrict__ moving, const float* __restrict__ fl
 // global memory instead.  No registers are tied up by bytes in flight, which is what lets an
 // HBM-bound gather approach copy bandwidth.  Needs W % 4 == 0, planar flow (stride 1 along x) and
 // 16-byte aligned bases (tensor-map rules); otherwise the direct kernel above runs.
-constexpr int WT_TH = 16, WT_TW = 64;      // output tile
-constexpr int WT_BH = 32, WT_BW = 96;      // source window (box of the image tensor map)
+#ifndef SSTEM_WARP_TH
+#define SSTEM_WARP_TH 8
+#endif
+#ifndef SSTEM_WARP_BH
+#define SSTEM_WARP_BH 24
+#endif
+constexpr int WT_TH = SSTEM_WARP_TH, WT_TW = 64;      // output tile; WT_TH * 16 threads, 4 pixels each
+constexpr int WT_BH = SSTEM_WARP_BH, WT_BW = 96;      // source window (box of the image tensor map)
+constexpr int WT_SH = WT_TH + 4, WT_SW = 72;          // small window, tried first (smooth flows): 1.7x the tile
+constexpr int WT_THREADS = WT_TH * 16;
+constexpr int WT_HALF = WT_TH / 2;                    // a thread's two rows are WT_HALF apart
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
@@ -194,12 +203,13 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
 }
 
 #ifndef SSTEM_WARP_TMA_MINB
-#define SSTEM_WARP_TMA_MINB 3
+#define SSTEM_WARP_TMA_MINB 7
 #endif
 template <int CT>
-__global__ void __launch_bounds__(256, SSTEM_WARP_TMA_MINB)
+__global__ void __launch_bounds__(WT_THREADS, SSTEM_WARP_TMA_MINB)
 warp_torch_tma_kernel(const __grid_constant__ CUtensorMap map_fx, const __grid_constant__ CUtensorMap map_fy,
-                      const __grid_constant__ CUtensorMap map_im, const float* __restrict__ moving,
+                      const __grid_constant__ CUtensorMap map_im, const __grid_constant__ CUtensorMap map_im_small,
+                      const float* __restrict__ moving,
                       float* __restrict__ out, int H, int W) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* s_im = reinterpret_cast<float*>(smem_raw);                       // [CT][BH][BW]
@@ -223,7 +233,7 @@ warp_torch_tma_kernel(const __grid_constant__ CUtensorMap map_fx, const __grid_c
         tma_load_3d(s_fx, &map_fx, &bar[0], j00, i0, b);
         tma_load_3d(s_fy, &map_fy, &bar[0], j00, i0, b);
     }
-    // thread -> 4 pixels: rows (warp, warp + 8) x columns (lane, lane + 32).  Lanes walk along x,
+    // thread -> 4 pixels: rows (warp, warp + WT_HALF) x columns (lane, lane + 32).  Lanes walk along x,
     // so shared-memory reads are bank-conflict free and every global store is a full 128-byte line.
     const int warp = tid >> 5, lane = tid & 31;
     mbar_wait(&bar[0], 0);
@@ -234,7 +244,7 @@ warp_torch_tma_kernel(const __grid_constant__ CUtensorMap map_fx, const __grid_c
     int mnx = INT32_MAX, mny = INT32_MAX, mxx = INT32_MIN, mxy = INT32_MIN;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        const int r = warp + 8 * (q >> 1), cidx = lane + 32 * (q & 1);
+        const int r = warp + WT_HALF * (q >> 1), cidx = lane + 32 * (q & 1);
         const int i = i0 + r, j = j00 + cidx;
         const BilinearTap t = torch_tap(s_fx[r * WT_TW + cidx], s_fy[r * WT_TW + cidx], i, j, H, W);
         xa[q] = t.x0 - 1; ya[q] = t.y0 - 1;
@@ -255,13 +265,16 @@ warp_torch_tma_kernel(const __grid_constant__ CUtensorMap map_fx, const __grid_c
     __syncthreads();
     // the box must start on a 16-byte boundary in global memory: round the left edge down to 4 floats
     const int bx0 = s_box[0] & ~3, by0 = s_box[1], bx1 = s_box[2], by1 = s_box[3];
-    const bool fits = (bx1 - bx0 < WT_BW) && (by1 - by0 < WT_BH);
+    const bool small = (bx1 - bx0 < WT_SW) && (by1 - by0 < WT_SH);
+    const bool fits = small || ((bx1 - bx0 < WT_BW) && (by1 - by0 < WT_BH));
+    const int pitch = small ? WT_SW : WT_BW;            // block-uniform
+    const int cstride = small ? WT_SH * WT_SW : WT_BH * WT_BW;
     if (fits && tid == 0) {
-        mbar_expect_tx(&bar[1], (unsigned)(CT * WT_BH * WT_BW * sizeof(float)));
-        tma_load_3d(s_im, &map_im, &bar[1], bx0, by0, b * CT);
+        mbar_expect_tx(&bar[1], (unsigned)(CT * cstride * sizeof(float)));
+        tma_load_3d(s_im, small ? &map_im_small : &map_im, &bar[1], bx0, by0, b * CT);
     }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) offa[q] = (ya[q] - by0) * WT_BW + (xa[q] - bx0);
+    for (int q = 0; q < 4; ++q) offa[q] = (ya[q] - by0) * pitch + (xa[q] - bx0);
     const int64_t plane = (int64_t)H * W;
     float* obase = out + (int64_t)b * CT * plane;
     if (fits) {
@@ -270,13 +283,13 @@ warp_torch_tma_kernel(const __grid_constant__ CUtensorMap map_fx, const __grid_c
         for (int c = 0; c < CT; ++c) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const float* sp = s_im + c * (WT_BH * WT_BW) + offa[q];
-                const int dy = dys[q] * WT_BW;
+                const float* sp = s_im + c * cstride + offa[q];
+                const int dy = dys[q] * pitch;
                 const float Ia = sp[0], Ib = sp[dy], Ic = sp[dxs[q]], Id = sp[dy + dxs[q]];
                 float r = __fadd_rn(__fmul_rn(wa[q], Ia), __fmul_rn(wb[q], Ib));
                 r = __fadd_rn(r, __fmul_rn(wc[q], Ic));
                 r = __fadd_rn(r, __fmul_rn(wd[q], Id));
-                const int i = i0 + warp + 8 * (q >> 1), j = j00 + lane + 32 * (q & 1);
+                const int i = i0 + warp + WT_HALF * (q >> 1), j = j00 + lane + 32 * (q & 1);
                 if (i < H && j < W) __stcs(obase + c * plane + (int64_t)i * W + j, r);
             }
         }
@@ -297,7 +310,7 @@ warp_torch_tma_kernel(const __grid_constant__ CUtensorMap map_fx, const __grid_c
                 float r = __fadd_rn(__fmul_rn(wa[q], Ia), __fmul_rn(wb[q], Ib));
                 r = __fadd_rn(r, __fmul_rn(wc[q], Ic));
                 r = __fadd_rn(r, __fmul_rn(wd[q], Id));
-                const int i = i0 + warp + 8 * (q >> 1), j = j00 + lane + 32 * (q & 1);
+                const int i = i0 + warp + WT_HALF * (q >> 1), j = j00 + lane + 32 * (q & 1);
                 if (i < H && j < W) __stcs(obase + c * plane + (int64_t)i * W + j, r);
             }
         }
@@ -343,10 +356,11 @@ static int try_launch_warp_tma(const float* moving, const float* flow, const int
                                int64_t B, int64_t H, int64_t W, cudaStream_t s) {
     if ((W & 3) || fs[2] != 1 || !aligned16(moving) || !aligned16(flow) || !aligned16(out)) return -1000;
     if ((fs[0] & 3) || (fs[1] & 3) || (fs[3] & 3) || fs[1] < W || B > 65535 || (H + WT_TH - 1) / WT_TH > 65535) return -1000;
-    CUtensorMap mfx, mfy, mim;
+    CUtensorMap mfx, mfy, mim, mims;
     if (!make_map3(&mfx, flow, W, H, B, fs[1], fs[0], WT_TW, WT_TH, 1)) return -1000;
     if (!make_map3(&mfy, flow + fs[3], W, H, B, fs[1], fs[0], WT_TW, WT_TH, 1)) return -1000;
     if (!make_map3(&mim, moving, W, H, B * CT, W, H * W, WT_BW, WT_BH, CT)) return -1000;
+    if (!make_map3(&mims, moving, W, H, B * CT, W, H * W, WT_SW, WT_SH, CT)) return -1000;
     const size_t smem = (size_t)(CT * WT_BH * WT_BW + 2 * WT_TH * WT_TW) * sizeof(float) + 64;
     static bool done[16] = {};
     int dev = 0;
@@ -357,7 +371,7 @@ static int try_launch_warp_tma(const float* moving, const float* flow, const int
         done[dev & 15] = true;
     }
     dim3 grid((unsigned)((W + WT_TW - 1) / WT_TW), (unsigned)((H + WT_TH - 1) / WT_TH), (unsigned)B);
-    warp_torch_tma_kernel<CT><<<grid, 256, smem, s>>>(mfx, mfy, mim, moving, out, (int)H, (int)W);
+    warp_torch_tma_kernel<CT><<<grid, WT_THREADS, smem, s>>>(mfx, mfy, mim, mims, moving, out, (int)H, (int)W);
     count_launch();
     return finish_launch();
 }

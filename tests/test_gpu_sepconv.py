@@ -273,3 +273,17 @@ def test_other_device_stream_and_noncurrent_stream():
         got = _fwd(inp, v, h)
     s.synchronize()
     assert torch.equal(ref, got)
+
+
+def test_host_buffer_pipeline_matches_device_path():
+    """sepconv_forward_backward_host (chunked, multi-stream, pinned buffers) == the autograd op."""
+    pkg = _ops()
+    inp, v, h, g = cases.sepconv_inputs(5, 3, 24, 40, seed=77, kind="unit")
+    ti, tv, th, tg = (torch.from_numpy(a) for a in (inp, v, h, g))
+    out, gv, gh = pkg.sepconv_forward_backward_host(ti.pin_memory(), tv.pin_memory(), th.pin_memory(), tg.pin_memory(), chunk=2)
+    torch.cuda.synchronize()
+    ref_out, _, ref_gv, ref_gh = _bwd(*_cuda(inp, v, h, g), need_input=False)
+    assert torch.equal(out, ref_out.cpu()) and torch.equal(gv, ref_gv.cpu()) and torch.equal(gh, ref_gh.cpu())
+    only = pkg.sepconv_forward_backward_host(ti, tv, th)          # forward only, pageable memory
+    torch.cuda.synchronize()
+    assert torch.equal(only, ref_out.cpu())
