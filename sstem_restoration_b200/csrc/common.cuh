@@ -58,6 +58,8 @@ int launch_sepconv_bwd_taps_generic(const float* g, const float* in, const float
 int launch_sepconv_bwd_taps_k51(const float* g, const float* in, const float* v, const float* h,
                                 float* gv, float* gh,
                                 int64_t B, int64_t C, int64_t H, int64_t W, cudaStream_t s);
+int launch_sepconv_bwd_input_k51(const float* g, const float* v, const float* h, float* gi,
+                                 int64_t B, int64_t C, int64_t H, int64_t W, cudaStream_t s);
 int launch_sepconv_bwd_input_generic(const float* g, const float* v, const float* h, float* gi,
                                      int64_t B, int64_t C, int64_t H, int64_t W, int K, cudaStream_t s);
 

@@ -548,6 +548,176 @@ sepconv_bwd_taps_k51_kernel(const float* __restrict__ gout, const float* __restr
     }
 }
 
+// =====================================================================================
+// Backward w.r.t. the input (the adjoint of the forward; the reference never computes it):
+//   gi[c][y+fy][x+fx] += g[c][y][x] * v[fy][y][x] * h[fx][y][x]
+// The forward's lane mapping run "in reverse": at step s the lane forms, for each of its taps,
+//   q = sum over its R rows of h[row][tap] * (g[row] * v[fy = s-row][row])
+// (all operands in registers) and adds q to word x+fx of row s of a shared gi tile.
+// The adds are plain read-modify-writes, made race-free by construction:
+//   * inside a warp the 4 tap groups walk their taps in rotated order (group g starts 2g taps
+//     in), so the 32 lanes of one instruction always hit 32 different words;
+//   * the 4 warps run one step apart (warp w does step tau - w at time tau, a barrier per
+//     step), so at any time they work on 4 different rows.
+// The tile, (R+50) x (TILE_W+50) per channel, overlaps its neighbours' by 50, so it is
+// flushed with global atomics into a zero-initialised gi (the order of those few adds, hence
+// the last bit, may vary run to run).  2*C*K*(K+1) flop per pixel, like the forward.
+// =====================================================================================
+template <int CC, int R, int S>
+__device__ __forceinline__ void gi_step(float* __restrict__ trowA, int thr, bool g3,
+                                        const float2 (&g2)[CC][R / 2], const float2 (&h2)[R / 2][13],
+                                        const float2 (&v2)[R / 2]) {
+    using Gm = Geo<4, R>;
+    constexpr int NT = 13;
+    constexpr int CH = Gm::ROWS * Gm::PITCH;            // channel stride of the tile
+    // slot t of tap group g holds tap 4*((t + 2g) mod 13) + g; its word is trowA[4t] before the
+    // wrap (t < thr = 13 - 2g) and trowA[4t - 52] after it
+    float* trowB = trowA - 52;
+    float2 a2[CC][Gm::NP];
+#pragma unroll
+    for (int c = 0; c < CC; ++c)
+#pragma unroll
+        for (int pp = 0; pp < Gm::NP; ++pp) a2[c][pp] = __fmul2_rn(g2[c][pp], v2[pp]);   // v = 0 where fy is out of range
+    // One slot at a time: within a slot the 32 lanes (and the CC channel planes) hit distinct
+    // words, so the read-modify-writes below are race free; ACROSS slots lanes do revisit words,
+    // which is safe because a warp's shared-memory accesses execute in program order -- the
+    // __syncwarp() keeps the compiler from hoisting the next slot's loads above these stores.
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+        float* wp = (t < thr ? trowA : trowB) + 4 * t;
+        float old[CC];
+#pragma unroll
+        for (int c = 0; c < CC; ++c) old[c] = wp[c * CH];
+#pragma unroll
+        for (int c = 0; c < CC; ++c) {
+            float2 q2 = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int pp = 0; pp < Gm::NP; ++pp) {
+                if (S >= 0 && (S < 2 * pp || S > 2 * pp + K51)) continue;
+                q2 = __ffma2_rn(h2[pp][t], a2[c][pp], q2);
+            }
+            old[c] += q2.x + q2.y;
+        }
+        if (!(t == 6 && g3)) {                          // (g == 3, slot 6) would be tap 51
+#pragma unroll
+            for (int c = 0; c < CC; ++c) wp[c * CH] = old[c];
+        }
+        __syncwarp();                                   // the next slot may read words other lanes just wrote
+    }
+}
+
+template <int CC, int R, bool VEC>
+__global__ void __launch_bounds__(128, 2)
+sepconv_bwd_input_k51_kernel(const float* __restrict__ gout, const float* __restrict__ v,
+                             const float* __restrict__ h, float* __restrict__ gi,
+                             int C, int c0, int H, int W) {
+    constexpr int G = 4;
+    using Gm = Geo<G, R>;
+    static_assert(Gm::NT == 13, "rotation scheme is written for 4 tap groups of 13");
+    extern __shared__ __align__(16) float tile[];      // [CC][ROWS][PITCH] gi accumulators + 4 warps x v ring
+    const int IW = W + K51 - 1, IH = H + K51 - 1;
+    const int x0 = blockIdx.x * Gm::TILE_W, y0 = blockIdx.y * R;
+    const int64_t b = blockIdx.z;
+    const int64_t plane = (int64_t)H * W;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < CC * Gm::ROWS * Gm::PITCH; i += 128) tile[i] = 0.f;
+    cp_async_commit();                                  // group 0 (empty): keeps the ring's group arithmetic
+
+    const int warp = tid >> 5, lane = tid & 31;
+    const int pg = lane / G, g = lane % G;
+    const int xl = warp * Gm::COLS + pg;
+    const int x = min(x0 + xl, W - 1);
+    const bool g3 = (g == 3);
+    const bool col_ok = (x0 + xl < W);
+
+    VRing<G, R, VEC> vr;
+    vr.init(tile + CC * Gm::ROWS * Gm::PITCH + warp * (VDEPTH * Gm::SLOT), v, b * K51 * plane, plane,
+            y0, x0 + warp * Gm::COLS, H, W, lane);
+#pragma unroll
+    for (int st = 0; st < VDEPTH - 1; ++st) vr.issue();
+
+    // horizontal taps in rotated slot order: slot t <- tap 4*((t + 2g) mod 13) + g
+    float2 h2[Gm::NP][13], g2[CC][Gm::NP];
+    {
+        const float* hp[R];
+#pragma unroll
+        for (int p = 0; p < R; ++p) hp[p] = h + (b * K51 + g) * plane + (int64_t)min(y0 + p, H - 1) * W + x;
+#pragma unroll
+        for (int t = 0; t < 13; ++t) {
+            int m = t + 2 * g;
+            m = m >= 13 ? m - 13 : m;
+            m = (m == 12 && g3) ? 11 : m;               // tap 51 does not exist: read tap 47, its q is discarded
+            const int64_t off = (int64_t)(4 * m) * plane;
+#pragma unroll
+            for (int pp = 0; pp < Gm::NP; ++pp)
+                h2[pp][t] = make_float2(__ldg(hp[2 * pp] + off), __ldg(hp[2 * pp + 1] + off));
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < CC; ++c)
+#pragma unroll
+        for (int pp = 0; pp < Gm::NP; ++pp) {
+            const float* gp = gout + (b * C + c0 + c) * plane + x;
+            const int ya = y0 + 2 * pp, yb = ya + 1;
+            g2[c][pp].x = (col_ok && ya < H) ? __ldg(gp + (int64_t)ya * W) : 0.f;   // outside the image: no contribution
+            g2[c][pp].y = (col_ok && yb < H) ? __ldg(gp + (int64_t)yb * W) : 0.f;
+        }
+    cp_async_wait<VDEPTH - 2>();
+    __syncthreads();                                    // tile zeroed
+
+    float2 vcur[Gm::NP], vnext[Gm::NP];
+    vr.read(vcur);
+    float* trow = tile + xl + g + 8 * g;                // word of slot 0: x + g + 4*(2g)
+    const int thr = 13 - 2 * g;
+    auto advance = [&]() {
+        cp_async_wait<VDEPTH - 3>();
+        __syncwarp();
+        vr.issue();
+        vr.read(vnext);
+    };
+    for (int i = 0; i < warp; ++i) __syncthreads();     // skew: warp w runs w steps behind warp 0
+#define SSTEM_GI_EDGE_STEP(S)                                                       \
+    if ((S) < R - 1 || ((S) >= K51 && (S) < Gm::ROWS)) {                            \
+        advance();                                                                  \
+        gi_step<CC, R, S>(trow, thr, g3, g2, h2, vcur);                             \
+        _Pragma("unroll") for (int pp = 0; pp < Gm::NP; ++pp) vcur[pp] = vnext[pp]; \
+        trow += Gm::PITCH;                                                          \
+        __syncthreads();                                                            \
+    }
+    SSTEM_GI_EDGE_STEP(0) SSTEM_GI_EDGE_STEP(1) SSTEM_GI_EDGE_STEP(2) SSTEM_GI_EDGE_STEP(3)
+    SSTEM_GI_EDGE_STEP(4) SSTEM_GI_EDGE_STEP(5) SSTEM_GI_EDGE_STEP(6)
+#pragma unroll 1
+    for (int s = R - 1; s < K51; ++s) {
+        advance();
+        gi_step<CC, R, -1>(trow, thr, g3, g2, h2, vcur);
+#pragma unroll
+        for (int pp = 0; pp < Gm::NP; ++pp) vcur[pp] = vnext[pp];
+        trow += Gm::PITCH;
+        __syncthreads();
+    }
+    SSTEM_GI_EDGE_STEP(51) SSTEM_GI_EDGE_STEP(52) SSTEM_GI_EDGE_STEP(53) SSTEM_GI_EDGE_STEP(54)
+    SSTEM_GI_EDGE_STEP(55) SSTEM_GI_EDGE_STEP(56) SSTEM_GI_EDGE_STEP(57)
+#undef SSTEM_GI_EDGE_STEP
+    for (int i = warp; i < 3; ++i) __syncthreads();     // every warp passes the same number of barriers
+    __syncthreads();
+
+    // ---- flush: the tile overlaps its neighbours', so add into the (pre-zeroed) gradient -----------
+    constexpr int FW = Gm::TILE_W + K51 - 1;            // columns that can be non-zero
+    if (tid < FW && x0 + tid < IW) {                    // a thread owns one column and walks down the rows
+#pragma unroll 1
+        for (int c = 0; c < CC; ++c) {
+            const float* tp = tile + c * Gm::ROWS * Gm::PITCH + tid;
+            float* gp = gi + ((b * C + c0 + c) * (int64_t)IH + y0) * IW + x0 + tid;
+            const int rmax = min(Gm::ROWS, IH - y0);
+#pragma unroll 2
+            for (int r = 0; r < rmax; ++r) {
+                const float val = tp[r * Gm::PITCH];
+                if (val != 0.f) atomicAdd(gp + (int64_t)r * IW, val);
+            }
+        }
+    }
+}
+
 // ---- host side ------------------------------------------------------------------------------
 template <typename Kern>
 int set_smem_once(Kern kern, size_t smem, bool* done) {
@@ -660,6 +830,37 @@ int launch_sepconv_bwd_taps_k51(const float* g, const float* in, const float* v,
     if (gv && gh) return launch_bwd_all<true, true>(g, in, v, h, gv, gh, B, (int)C, (int)H, (int)W, s);
     if (gv) return launch_bwd_all<true, false>(g, in, v, h, gv, gh, B, (int)C, (int)H, (int)W, s);
     return launch_bwd_all<false, true>(g, in, v, h, gv, gh, B, (int)C, (int)H, (int)W, s);
+}
+
+int launch_sepconv_bwd_input_k51(const float* g, const float* v, const float* h, float* gi,
+                                 int64_t B, int64_t C, int64_t H, int64_t W, cudaStream_t s) {
+    constexpr int G = 4, R = 8;
+    if (B > 65535 || (H + R - 1) / R > 65535)
+        return launch_sepconv_bwd_input_generic(g, v, h, gi, B, C, H, W, 51, s);
+    cudaError_t e = cudaMemsetAsync(gi, 0, (size_t)B * C * (H + K51 - 1) * (W + K51 - 1) * sizeof(float), s);
+    if (e != cudaSuccess) return (int)e;
+    const bool vec = ((W & 3) == 0) && aligned16(v);
+    dim3 grid((unsigned)((W + Geo<G, R>::TILE_W - 1) / Geo<G, R>::TILE_W), (unsigned)((H + R - 1) / R), (unsigned)B);
+    int c0 = 0;
+    while (c0 < C) {
+        const int cc = (C - c0) < 3 ? (int)(C - c0) : 3;
+#define SSTEM_GI_LAUNCH(CC_, VEC_)                                                                   \
+    {                                                                                                 \
+        constexpr size_t smem = smem_bytes<G, R, CC_>();                                              \
+        static bool done[16] = {};                                                                    \
+        auto kern = sepconv_bwd_input_k51_kernel<CC_, R, VEC_>;                                    \
+        if (int err = set_smem_once(kern, smem, done)) return err;                                    \
+        kern<<<grid, 128, smem, s>>>(g, v, h, gi, (int)C, c0, (int)H, (int)W);                        \
+    }
+        if (cc == 3) { if (vec) SSTEM_GI_LAUNCH(3, true) else SSTEM_GI_LAUNCH(3, false) }
+        else if (cc == 2) { if (vec) SSTEM_GI_LAUNCH(2, true) else SSTEM_GI_LAUNCH(2, false) }
+        else { if (vec) SSTEM_GI_LAUNCH(1, true) else SSTEM_GI_LAUNCH(1, false) }
+#undef SSTEM_GI_LAUNCH
+        count_launch();
+        if (int err = finish_launch()) return err;
+        c0 += cc;
+    }
+    return 0;
 }
 
 }  // namespace sstem

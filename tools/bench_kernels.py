@@ -53,11 +53,11 @@ def main():
             print(json.dumps({"op": "bwd_taps", "shape": [B, C, H, W], "ms": round(ms, 4), "gpix_s": round(px / ms / 1e6, 3),
                               "tflops_alg": round(fl / ms / 1e9, 2), "frac_probe": round(fl / ms / 1e9 / peak, 3)}))
             del gv, gh
-        if "gi" in what and px <= 16 * 512 * 512:
+        if "gi" in what:
             gi = torch.empty_like(inp)
             ms = timeit(lambda: lib.sstem_sepconv_backward(g.data_ptr(), inp.data_ptr(), v.data_ptr(), h.data_ptr(), gi.data_ptr(), None, None, B, C, H, W, K, 0, st), reps=2, warm=1)
             fl = 2 * C * K * (K + 1) * px
-            print(json.dumps({"op": "bwd_input", "shape": [B, C, H, W], "ms": round(ms, 4), "gpix_s": round(px / ms / 1e6, 3), "tflops_alg": round(fl / ms / 1e9, 2)}))
+            print(json.dumps({"op": "bwd_input", "shape": [B, C, H, W], "ms": round(ms, 4), "gpix_s": round(px / ms / 1e6, 3), "tflops_alg": round(fl / ms / 1e9, 2), "frac_probe": round(fl / ms / 1e9 / peak, 3)}))
         del inp, v, h, g, out
         torch.cuda.empty_cache()
     if "warp" in what:
