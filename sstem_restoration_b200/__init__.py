@@ -16,11 +16,11 @@ from .sepconv import (  # noqa: F401
     SeparableConvolution, FunctionSepconv, ModuleSepconv, set_strict_order,
 )
 from .warp import SpatialTransformation, image_warp  # noqa: F401
-from .host import sepconv_forward_backward_host  # noqa: F401
+from .host import sepconv_forward_backward_host, join_host_pipeline  # noqa: F401
 from . import shard, synth  # noqa: F401
 
 __all__ = [
     "SeparableConvolution", "FunctionSepconv", "ModuleSepconv", "set_strict_order",
-    "SpatialTransformation", "image_warp", "sepconv_forward_backward_host", "SstemError", "launch_count", "fp32_peak_probe",
+    "SpatialTransformation", "image_warp", "sepconv_forward_backward_host", "join_host_pipeline", "SstemError", "launch_count", "fp32_peak_probe",
     "shard", "synth",
 ]

@@ -50,10 +50,12 @@ def _resources(device, n):
 def sepconv_forward_backward_host(input: torch.Tensor, vertical: torch.Tensor, horizontal: torch.Tensor,
                                   grad_output: Optional[torch.Tensor] = None, *, device=None, chunk: int = 2,
                                   n_streams: int = 3,
-                                  out: Optional[Tuple[torch.Tensor, ...]] = None):
+                                  out: Optional[Tuple[torch.Tensor, ...]] = None, join: bool = True):
     """input [B,C,H+50,W+50], vertical/horizontal [B,51,H,W], grad_output [B,C,H,W]: CPU float32,
     ideally pinned.  Returns CPU (pinned) ``output`` or ``(output, grad_vertical, grad_horizontal)``.
-    ``out`` may supply the pinned result tensors to reuse."""
+    ``out`` may supply the pinned result tensors to reuse.  With ``join=False`` the call only queues
+    the work (back-to-back calls then overlap one call's downloads with the next call's uploads);
+    call :func:`join_host_pipeline` (or synchronize the device) before reading the results."""
     if not torch.cuda.is_available():
         raise _lib.SstemError("sepconv_forward_backward_host: no CUDA device; there is no CPU fallback")
     for t in (input, vertical, horizontal):
@@ -72,9 +74,6 @@ def sepconv_forward_backward_host(input: torch.Tensor, vertical: torch.Tensor, h
         res = list(out)
     lib = _lib.load()
     streams, spaces = _resources(dev, n_streams)
-    cur = torch.cuda.current_stream(dev)
-    for s in streams:
-        s.wait_stream(cur)
     with torch.cuda.device(dev):
         for ci, lo in enumerate(range(0, B, chunk)):
             hi = min(B, lo + chunk)
@@ -85,22 +84,36 @@ def sepconv_forward_backward_host(input: torch.Tensor, vertical: torch.Tensor, h
                 d_v = ws.get("v", (n, K, H, W))
                 d_h = ws.get("h", (n, K, H, W))
                 d_out = ws.get("out", (n, C, H, W))
+                # all uploads of the chunk first, then the kernels, then all downloads: the copy engines
+                # serve their queues in issue order, so a copy that waits on a kernel must not sit in
+                # front of the next chunk's uploads
                 d_in.copy_(input[lo:hi], non_blocking=True)
                 d_v.copy_(vertical[lo:hi], non_blocking=True)
                 d_h.copy_(horizontal[lo:hi], non_blocking=True)
-                _lib.check(lib.sstem_sepconv_forward(d_in.data_ptr(), d_v.data_ptr(), d_h.data_ptr(), d_out.data_ptr(),
-                                                     n, C, H, W, K, 0, s.cuda_stream), "sstem_sepconv_forward")
-                res[0][lo:hi].copy_(d_out, non_blocking=True)
                 if want_grad:
                     d_g = ws.get("g", (n, C, H, W))
                     d_gv = ws.get("gv", (n, K, H, W))
                     d_gh = ws.get("gh", (n, K, H, W))
                     d_g.copy_(grad_output[lo:hi], non_blocking=True)
+                _lib.check(lib.sstem_sepconv_forward(d_in.data_ptr(), d_v.data_ptr(), d_h.data_ptr(), d_out.data_ptr(),
+                                                     n, C, H, W, K, 0, s.cuda_stream), "sstem_sepconv_forward")
+                if want_grad:
                     _lib.check(lib.sstem_sepconv_backward(d_g.data_ptr(), d_in.data_ptr(), d_v.data_ptr(), d_h.data_ptr(),
                                                           None, d_gv.data_ptr(), d_gh.data_ptr(), n, C, H, W, K, 0,
                                                           s.cuda_stream), "sstem_sepconv_backward")
+                res[0][lo:hi].copy_(d_out, non_blocking=True)
+                if want_grad:
                     res[1][lo:hi].copy_(d_gv, non_blocking=True)
                     res[2][lo:hi].copy_(d_gh, non_blocking=True)
+    if join:
+        join_host_pipeline(dev, n_streams)
+    return tuple(res) if want_grad else res[0]
+
+
+def join_host_pipeline(device=None, n_streams: int = 3) -> None:
+    """Make the current stream wait for everything queued by sepconv_forward_backward_host."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    streams, _ = _resources(dev, n_streams)
+    cur = torch.cuda.current_stream(dev)
     for s in streams:
         cur.wait_stream(s)
-    return tuple(res) if want_grad else res[0]
