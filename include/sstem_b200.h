@@ -46,6 +46,13 @@ extern "C" {
  * inner, one accumulator, (in*v) then fma with h -- kernel.cu:45-49): bit-exact
  * with the reference kernel, ~2x the arithmetic.  Verification mode. */
 #define SSTEM_SEPCONV_STRICT_ORDER  1u
+/* The caller asserts that all `channels` planes of `input` are identical copies -- what the
+ * reference's callers feed it (grayscale sections replicated x3:
+ * sff_scripts_interp/data/data_provider.py:136-137, inference.py:71-77).  The forward then
+ * computes one plane and writes `channels` copies (bit-identical to the general path); the tap
+ * gradients use t = (sum_c g_c) * in_0 (same value up to fp32 rounding).  51 taps only; ignored by
+ * the grad_input path (its result differs per channel through grad_output). */
+#define SSTEM_SEPCONV_GRAY_REPLICATED 2u
 
 /*
  * out[b,c,y,x] = sum_{fy,fx} in[b,c,y+fy,x+fx] * v[b,fy,y,x] * h[b,fx,y,x]

@@ -13,14 +13,14 @@ __graft_entry__.build) every operator raises.
 """
 from ._lib import SstemError, launch_count, fp32_peak_probe  # noqa: F401
 from .sepconv import (  # noqa: F401
-    SeparableConvolution, FunctionSepconv, ModuleSepconv, set_strict_order,
+    SeparableConvolution, FunctionSepconv, ModuleSepconv, set_strict_order, set_gray_replicated,
 )
 from .warp import SpatialTransformation, image_warp  # noqa: F401
 from .host import sepconv_forward_backward_host, join_host_pipeline  # noqa: F401
 from . import shard, synth  # noqa: F401
 
 __all__ = [
-    "SeparableConvolution", "FunctionSepconv", "ModuleSepconv", "set_strict_order",
+    "SeparableConvolution", "FunctionSepconv", "ModuleSepconv", "set_strict_order", "set_gray_replicated",
     "SpatialTransformation", "image_warp", "sepconv_forward_backward_host", "join_host_pipeline", "SstemError", "launch_count", "fp32_peak_probe",
     "shard", "synth",
 ]

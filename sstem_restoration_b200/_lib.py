@@ -22,6 +22,7 @@ _c_p = ctypes.c_void_p
 
 SEPCONV_DEFAULT = 0
 SEPCONV_STRICT_ORDER = 1
+SEPCONV_GRAY_REPLICATED = 2
 LAYOUT_NCHW = 0
 LAYOUT_NHWC = 1
 PIX_U8 = 0

@@ -20,13 +20,14 @@ extern "C" int sstem_sepconv_forward(const float* input, const float* vertical, 
                                      int32_t K, uint32_t flags, void* stream) {
     if (!input || !vertical || !horizontal || !output) return SSTEM_E_NULL;
     if (int e = check_sepconv_dims(B, C, H, W, K)) return e;
-    if (flags & ~SSTEM_SEPCONV_STRICT_ORDER) return SSTEM_E_FLAG;
+    if (flags & ~(SSTEM_SEPCONV_STRICT_ORDER | SSTEM_SEPCONV_GRAY_REPLICATED)) return SSTEM_E_FLAG;
     if (!aligned4(input) || !aligned4(vertical) || !aligned4(horizontal) || !aligned4(output)) return SSTEM_E_ALIGN;
     DeviceGuard guard(output);
     if (guard.err) return guard.err;
     cudaStream_t s = (cudaStream_t)stream;
     const bool strict = flags & SSTEM_SEPCONV_STRICT_ORDER;
-    if (K == 51 && !strict) return launch_sepconv_fwd_k51(input, vertical, horizontal, output, B, C, H, W, s);
+    const bool gray = flags & SSTEM_SEPCONV_GRAY_REPLICATED;
+    if (K == 51 && !strict) return launch_sepconv_fwd_k51(input, vertical, horizontal, output, B, C, H, W, gray, s);
     return launch_sepconv_fwd_generic(input, vertical, horizontal, output, B, C, H, W, K, strict, s);
 }
 
@@ -38,7 +39,7 @@ extern "C" int sstem_sepconv_backward(const float* grad_output, const float* inp
     if (!grad_output || !input || !vertical || !horizontal) return SSTEM_E_NULL;
     if (!grad_input && !grad_vertical && !grad_horizontal) return SSTEM_E_NULL;
     if (int e = check_sepconv_dims(B, C, H, W, K)) return e;
-    if (flags & ~SSTEM_SEPCONV_STRICT_ORDER) return SSTEM_E_FLAG;
+    if (flags & ~(SSTEM_SEPCONV_STRICT_ORDER | SSTEM_SEPCONV_GRAY_REPLICATED)) return SSTEM_E_FLAG;
     if (!aligned4(grad_output) || !aligned4(input) || !aligned4(vertical) || !aligned4(horizontal) ||
         !aligned4(grad_input) || !aligned4(grad_vertical) || !aligned4(grad_horizontal))
         return SSTEM_E_ALIGN;
@@ -49,7 +50,8 @@ extern "C" int sstem_sepconv_backward(const float* grad_output, const float* inp
     int e = 0;
     if (grad_vertical || grad_horizontal) {
         if (K == 51)
-            e = launch_sepconv_bwd_taps_k51(grad_output, input, vertical, horizontal, grad_vertical, grad_horizontal, B, C, H, W, s);
+            e = launch_sepconv_bwd_taps_k51(grad_output, input, vertical, horizontal, grad_vertical, grad_horizontal, B, C, H, W,
+                                            (flags & SSTEM_SEPCONV_GRAY_REPLICATED) != 0, s);
         else
             e = launch_sepconv_bwd_taps_generic(grad_output, input, vertical, horizontal, grad_vertical, grad_horizontal, B, C, H, W, K, s);
         if (e) return e;

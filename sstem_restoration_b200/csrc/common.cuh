@@ -51,13 +51,13 @@ int launch_sepconv_fwd_generic(const float* in, const float* v, const float* h, 
                                int64_t B, int64_t C, int64_t H, int64_t W, int K, bool strict,
                                cudaStream_t s);
 int launch_sepconv_fwd_k51(const float* in, const float* v, const float* h, float* out,
-                           int64_t B, int64_t C, int64_t H, int64_t W, cudaStream_t s);
+                           int64_t B, int64_t C, int64_t H, int64_t W, bool gray, cudaStream_t s);
 int launch_sepconv_bwd_taps_generic(const float* g, const float* in, const float* v, const float* h,
                                     float* gv, float* gh,
                                     int64_t B, int64_t C, int64_t H, int64_t W, int K, cudaStream_t s);
 int launch_sepconv_bwd_taps_k51(const float* g, const float* in, const float* v, const float* h,
                                 float* gv, float* gh,
-                                int64_t B, int64_t C, int64_t H, int64_t W, cudaStream_t s);
+                                int64_t B, int64_t C, int64_t H, int64_t W, bool gray, cudaStream_t s);
 int launch_sepconv_bwd_input_k51(const float* g, const float* v, const float* h, float* gi,
                                  int64_t B, int64_t C, int64_t H, int64_t W, cudaStream_t s);
 int launch_sepconv_bwd_input_generic(const float* g, const float* v, const float* h, float* gi,

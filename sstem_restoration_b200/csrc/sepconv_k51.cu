@@ -268,7 +268,7 @@ template <int CC, int G, int R, bool VEC, bool PAIR>
 __global__ void __launch_bounds__(128, 2)
 sepconv_fwd_k51_kernel(const float* __restrict__ in, const float* __restrict__ v,
                        const float* __restrict__ h, float* __restrict__ out,
-                       int C, int c0, int H, int W) {
+                       int C, int c0, int H, int W, int replicas) {
     using Gm = Geo<G, R>;
     extern __shared__ __align__(16) float tile[];      // [CC][ROWS][PITCH] + 4 warps x v ring
     const int IW = W + K51 - 1, IH = H + K51 - 1;
@@ -350,7 +350,11 @@ sepconv_fwd_k51_kernel(const float* __restrict__ in, const float* __restrict__ v
 #pragma unroll
             for (int j = 0; j < PER; ++j) {
                 const int p = g * PER + j;
-                if (p < R && y0 + p < H) ob[(int64_t)p * W] = val[j];
+                if (p < R && y0 + p < H) {
+                    ob[(int64_t)p * W] = val[j];
+                    // gray x3 shortcut: the input planes are identical copies, so are the outputs
+                    for (int rc = 1; rc < replicas; ++rc) ob[(int64_t)rc * H * W + (int64_t)p * W] = val[j];
+                }
             }
         }
     }
@@ -428,7 +432,7 @@ __global__ void __launch_bounds__(128, 2)
 sepconv_bwd_taps_k51_kernel(const float* __restrict__ gout, const float* __restrict__ in,
                             const float* __restrict__ v, const float* __restrict__ h,
                             float* __restrict__ gv, float* __restrict__ gh,
-                            int C, int c0, int H, int W, int accumulate) {
+                            int C, int c0, int H, int W, int accumulate, int replicas) {
     using Gm = Geo<G, R>;
     constexpr int NP = Gm::NP, NT = Gm::NT;
     static_assert(R == G, "the per-step gv reduce maps row p to lane g == p");
@@ -474,6 +478,11 @@ sepconv_bwd_taps_k51_kernel(const float* __restrict__ gout, const float* __restr
             // rows / columns outside the image get g = 0: they then contribute nothing
             g2[c][pp].x = (col_ok && ya < H) ? __ldg(gp + (int64_t)ya * W) : 0.f;
             g2[c][pp].y = (col_ok && yb < H) ? __ldg(gp + (int64_t)yb * W) : 0.f;
+            // gray x3 shortcut: identical input planes => t = (sum_c g_c) * P
+            for (int rc = 1; rc < replicas; ++rc) {
+                g2[c][pp].x += (col_ok && ya < H) ? __ldg(gp + rc * plane + (int64_t)ya * W) : 0.f;
+                g2[c][pp].y += (col_ok && yb < H) ? __ldg(gp + rc * plane + (int64_t)yb * W) : 0.f;
+            }
         }
 
     cp_async_wait<VDEPTH - 2>();
@@ -739,65 +748,67 @@ constexpr size_t smem_bytes() {
 
 template <int CC, bool VEC, bool PAIR>
 int launch_fwd_variant(const float* in, const float* v, const float* h, float* out,
-                       int64_t B, int C, int c0, int H, int W, cudaStream_t s) {
+                       int64_t B, int C, int c0, int H, int W, int replicas, cudaStream_t s) {
     constexpr int G = SSTEM_FWD_G, R = SSTEM_FWD_R;
     constexpr size_t smem = smem_bytes<G, R, CC>();
     static bool done[16] = {};
     auto kern = sepconv_fwd_k51_kernel<CC, G, R, VEC, PAIR>;
     if (int e = set_smem_once(kern, smem, done)) return e;
     dim3 grid((unsigned)((W + Geo<G, R>::TILE_W - 1) / Geo<G, R>::TILE_W), (unsigned)((H + R - 1) / R), (unsigned)B);
-    kern<<<grid, 128, smem, s>>>(in, v, h, out, C, c0, H, W);
+    kern<<<grid, 128, smem, s>>>(in, v, h, out, C, c0, H, W, replicas);
     count_launch();
     return finish_launch();
 }
 
 template <int CC>
 int launch_fwd_chunk(const float* in, const float* v, const float* h, float* out,
-                     int64_t B, int C, int c0, int H, int W, cudaStream_t s) {
+                     int64_t B, int C, int c0, int H, int W, int replicas, cudaStream_t s) {
     const bool vec = ((W & 3) == 0) && aligned16(v);
     const bool pair = (((W + K51 - 1) & 1) == 0) && ((reinterpret_cast<uintptr_t>(in) & 7u) == 0);
-    if (vec && pair) return launch_fwd_variant<CC, true, true>(in, v, h, out, B, C, c0, H, W, s);
-    if (vec) return launch_fwd_variant<CC, true, false>(in, v, h, out, B, C, c0, H, W, s);
-    if (pair) return launch_fwd_variant<CC, false, true>(in, v, h, out, B, C, c0, H, W, s);
-    return launch_fwd_variant<CC, false, false>(in, v, h, out, B, C, c0, H, W, s);
+    if (vec && pair) return launch_fwd_variant<CC, true, true>(in, v, h, out, B, C, c0, H, W, replicas, s);
+    if (vec) return launch_fwd_variant<CC, true, false>(in, v, h, out, B, C, c0, H, W, replicas, s);
+    if (pair) return launch_fwd_variant<CC, false, true>(in, v, h, out, B, C, c0, H, W, replicas, s);
+    return launch_fwd_variant<CC, false, false>(in, v, h, out, B, C, c0, H, W, replicas, s);
 }
 
 template <int CC, bool VEC, bool PAIR, bool WV, bool WH>
 int launch_bwd_variant(const float* g, const float* in, const float* v, const float* h, float* gv, float* gh,
-                       int64_t B, int C, int c0, int H, int W, int accumulate, cudaStream_t s) {
+                       int64_t B, int C, int c0, int H, int W, int accumulate, int replicas, cudaStream_t s) {
     constexpr int G = SSTEM_BWD_G, R = SSTEM_BWD_R;
     constexpr size_t smem = smem_bytes<G, R, CC>();
     static bool done[16] = {};
     auto kern = sepconv_bwd_taps_k51_kernel<CC, G, R, VEC, PAIR, WV, WH>;
     if (int e = set_smem_once(kern, smem, done)) return e;
     dim3 grid((unsigned)((W + Geo<G, R>::TILE_W - 1) / Geo<G, R>::TILE_W), (unsigned)((H + R - 1) / R), (unsigned)B);
-    kern<<<grid, 128, smem, s>>>(g, in, v, h, gv, gh, C, c0, H, W, accumulate);
+    kern<<<grid, 128, smem, s>>>(g, in, v, h, gv, gh, C, c0, H, W, accumulate, replicas);
     count_launch();
     return finish_launch();
 }
 
 template <int CC, bool WV, bool WH>
 int launch_bwd_chunk(const float* g, const float* in, const float* v, const float* h, float* gv, float* gh,
-                     int64_t B, int C, int c0, int H, int W, int accumulate, cudaStream_t s) {
+                     int64_t B, int C, int c0, int H, int W, int accumulate, int replicas, cudaStream_t s) {
     const bool vec = ((W & 3) == 0) && aligned16(v);
     const bool pair = (((W + K51 - 1) & 1) == 0) && ((reinterpret_cast<uintptr_t>(in) & 7u) == 0);
-    if (vec && pair) return launch_bwd_variant<CC, true, true, WV, WH>(g, in, v, h, gv, gh, B, C, c0, H, W, accumulate, s);
-    if (vec) return launch_bwd_variant<CC, true, false, WV, WH>(g, in, v, h, gv, gh, B, C, c0, H, W, accumulate, s);
-    if (pair) return launch_bwd_variant<CC, false, true, WV, WH>(g, in, v, h, gv, gh, B, C, c0, H, W, accumulate, s);
-    return launch_bwd_variant<CC, false, false, WV, WH>(g, in, v, h, gv, gh, B, C, c0, H, W, accumulate, s);
+    if (vec && pair) return launch_bwd_variant<CC, true, true, WV, WH>(g, in, v, h, gv, gh, B, C, c0, H, W, accumulate, replicas, s);
+    if (vec) return launch_bwd_variant<CC, true, false, WV, WH>(g, in, v, h, gv, gh, B, C, c0, H, W, accumulate, replicas, s);
+    if (pair) return launch_bwd_variant<CC, false, true, WV, WH>(g, in, v, h, gv, gh, B, C, c0, H, W, accumulate, replicas, s);
+    return launch_bwd_variant<CC, false, false, WV, WH>(g, in, v, h, gv, gh, B, C, c0, H, W, accumulate, replicas, s);
 }
 
 template <bool WV, bool WH>
 int launch_bwd_all(const float* g, const float* in, const float* v, const float* h, float* gv, float* gh,
-                   int64_t B, int C, int H, int W, cudaStream_t s) {
+                   int64_t B, int C, int H, int W, bool gray, cudaStream_t s) {
+    if (gray && C > 1)                                     // identical planes: one channel, summed upstream gradient
+        return launch_bwd_chunk<1, WV, WH>(g, in, v, h, gv, gh, B, C, 0, H, W, 0, C, s);
     int c0 = 0;
     while (c0 < C) {                                       // channel chunks of <= 3; later chunks accumulate
         const int cc = (C - c0) < 3 ? (C - c0) : 3;
         const int acc = c0 > 0;
         int e;
-        if (cc == 3) e = launch_bwd_chunk<3, WV, WH>(g, in, v, h, gv, gh, B, C, c0, H, W, acc, s);
-        else if (cc == 2) e = launch_bwd_chunk<2, WV, WH>(g, in, v, h, gv, gh, B, C, c0, H, W, acc, s);
-        else e = launch_bwd_chunk<1, WV, WH>(g, in, v, h, gv, gh, B, C, c0, H, W, acc, s);
+        if (cc == 3) e = launch_bwd_chunk<3, WV, WH>(g, in, v, h, gv, gh, B, C, c0, H, W, acc, 1, s);
+        else if (cc == 2) e = launch_bwd_chunk<2, WV, WH>(g, in, v, h, gv, gh, B, C, c0, H, W, acc, 1, s);
+        else e = launch_bwd_chunk<1, WV, WH>(g, in, v, h, gv, gh, B, C, c0, H, W, acc, 1, s);
         if (e) return e;
         c0 += cc;
     }
@@ -807,16 +818,18 @@ int launch_bwd_all(const float* g, const float* in, const float* v, const float*
 }  // namespace
 
 int launch_sepconv_fwd_k51(const float* in, const float* v, const float* h, float* out,
-                           int64_t B, int64_t C, int64_t H, int64_t W, cudaStream_t s) {
+                           int64_t B, int64_t C, int64_t H, int64_t W, bool gray, cudaStream_t s) {
     if (B > 65535 || (H + SSTEM_FWD_R - 1) / SSTEM_FWD_R > 65535)   // grid.y / grid.z limits
         return launch_sepconv_fwd_generic(in, v, h, out, B, C, H, W, 51, false, s);
+    if (gray && C > 1)                                     // identical planes: compute one, write C copies
+        return launch_fwd_chunk<1>(in, v, h, out, B, (int)C, 0, (int)H, (int)W, (int)C, s);
     int c0 = 0;
     while (c0 < C) {                                       // channels in chunks of <= 3 (taps re-read per chunk)
         const int cc = (C - c0) < 3 ? (int)(C - c0) : 3;
         int e;
-        if (cc == 3) e = launch_fwd_chunk<3>(in, v, h, out, B, (int)C, c0, (int)H, (int)W, s);
-        else if (cc == 2) e = launch_fwd_chunk<2>(in, v, h, out, B, (int)C, c0, (int)H, (int)W, s);
-        else e = launch_fwd_chunk<1>(in, v, h, out, B, (int)C, c0, (int)H, (int)W, s);
+        if (cc == 3) e = launch_fwd_chunk<3>(in, v, h, out, B, (int)C, c0, (int)H, (int)W, 1, s);
+        else if (cc == 2) e = launch_fwd_chunk<2>(in, v, h, out, B, (int)C, c0, (int)H, (int)W, 1, s);
+        else e = launch_fwd_chunk<1>(in, v, h, out, B, (int)C, c0, (int)H, (int)W, 1, s);
         if (e) return e;
         c0 += cc;
     }
@@ -824,12 +837,12 @@ int launch_sepconv_fwd_k51(const float* in, const float* v, const float* h, floa
 }
 
 int launch_sepconv_bwd_taps_k51(const float* g, const float* in, const float* v, const float* h,
-                                float* gv, float* gh, int64_t B, int64_t C, int64_t H, int64_t W, cudaStream_t s) {
+                                float* gv, float* gh, int64_t B, int64_t C, int64_t H, int64_t W, bool gray, cudaStream_t s) {
     if (B > 65535 || (H + SSTEM_BWD_R - 1) / SSTEM_BWD_R > 65535)
         return launch_sepconv_bwd_taps_generic(g, in, v, h, gv, gh, B, C, H, W, 51, s);
-    if (gv && gh) return launch_bwd_all<true, true>(g, in, v, h, gv, gh, B, (int)C, (int)H, (int)W, s);
-    if (gv) return launch_bwd_all<true, false>(g, in, v, h, gv, gh, B, (int)C, (int)H, (int)W, s);
-    return launch_bwd_all<false, true>(g, in, v, h, gv, gh, B, (int)C, (int)H, (int)W, s);
+    if (gv && gh) return launch_bwd_all<true, true>(g, in, v, h, gv, gh, B, (int)C, (int)H, (int)W, gray, s);
+    if (gv) return launch_bwd_all<true, false>(g, in, v, h, gv, gh, B, (int)C, (int)H, (int)W, gray, s);
+    return launch_bwd_all<false, true>(g, in, v, h, gv, gh, B, (int)C, (int)H, (int)W, gray, s);
 }
 
 int launch_sepconv_bwd_input_k51(const float* g, const float* v, const float* h, float* gi,

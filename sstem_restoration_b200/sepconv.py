@@ -34,8 +34,35 @@ def set_strict_order(enabled: bool) -> None:
     _STRICT = bool(enabled)
 
 
-def _flags() -> int:
-    return _lib.SEPCONV_STRICT_ORDER if _STRICT else _lib.SEPCONV_DEFAULT
+_GRAY = os.environ.get("SSTEM_SEPCONV_GRAY", "off")        # off | assert | detect
+
+
+def set_gray_replicated(mode) -> None:
+    """Opt-in shortcut for the reference's actual inputs: grayscale sections replicated x3
+    (sff_scripts_interp/data/data_provider.py:136-137), i.e. identical channel planes.
+
+    ``"assert"``: the caller guarantees it; ``"detect"``: every forward compares the planes
+    (one small reduction + a host sync) and uses the shortcut only when they are equal;
+    ``"off"`` (default): always the general path.  Forward results are bit-identical either
+    way; tap gradients agree to fp32 rounding."""
+    global _GRAY
+    mode = {True: "assert", False: "off", None: "off"}.get(mode, mode)
+    if mode not in ("off", "assert", "detect"):
+        raise ValueError("mode must be 'off', 'assert' or 'detect'")
+    _GRAY = mode
+
+
+def _is_gray(input) -> bool:
+    if _GRAY == "off" or _STRICT or input.size(1) < 2:
+        return False
+    if _GRAY == "assert":
+        return True
+    return all(bool(torch.equal(input[:, 0], input[:, c])) for c in range(1, input.size(1)))
+
+
+def _flags(gray: bool = False) -> int:
+    f = _lib.SEPCONV_STRICT_ORDER if _STRICT else _lib.SEPCONV_DEFAULT
+    return f | (_lib.SEPCONV_GRAY_REPLICATED if gray else 0)
 
 
 def _stream_ptr(t: torch.Tensor) -> int:
@@ -59,7 +86,7 @@ def _check_shapes(input, vertical, horizontal, filter_size=None):
     return intFilterSize, intOutputHeight, intOutputWidth
 
 
-def _forward_impl(input, vertical, horizontal, filter_size):
+def _forward_impl(ctx, input, vertical, horizontal, filter_size):
     K, oh, ow = _check_shapes(input, vertical, horizontal, filter_size)
     if input.is_cuda == False:
         raise NotImplementedError()  # as the reference: CPU version not implemented
@@ -71,12 +98,14 @@ def _forward_impl(input, vertical, horizontal, filter_size):
     assert vertical.size(0) == input.size(0), "batch mismatch"
     B, C = input.size(0), input.size(1)
     output = torch.empty((B, C, oh, ow), dtype=input.dtype, device=input.device)
+    ctx.gray = False
     if output.numel() == 0:
         return output
+    ctx.gray = K == 51 and _is_gray(input)
     with torch.cuda.device_of(input):
         code = _lib.load().sstem_sepconv_forward(
             input.data_ptr(), vertical.data_ptr(), horizontal.data_ptr(), output.data_ptr(),
-            B, C, oh, ow, K, _flags(), _stream_ptr(input))
+            B, C, oh, ow, K, _flags(ctx.gray), _stream_ptr(input))
     _lib.check(code, "sstem_sepconv_forward")
     return output
 
@@ -99,7 +128,7 @@ def _backward_impl(ctx, grad_output):
                 grad_input.data_ptr() if need_in else None,
                 grad_vertical.data_ptr() if need_v else None,
                 grad_horizontal.data_ptr() if need_h else None,
-                B, C, oh, ow, K, _flags(), _stream_ptr(input))
+                B, C, oh, ow, K, _flags(getattr(ctx, "gray", False)), _stream_ptr(input))
         _lib.check(code, "sstem_sepconv_backward")
     return grad_input, grad_vertical, grad_horizontal
 
@@ -110,7 +139,7 @@ class SeparableConvolution(torch.autograd.Function):
     @staticmethod
     def forward(context, input, vertical, horizontal):
         context.save_for_backward(input, vertical, horizontal)
-        return _forward_impl(input, vertical, horizontal, 51)
+        return _forward_impl(context, input, vertical, horizontal, 51)
 
     @staticmethod
     def backward(context, grad_output):
@@ -125,7 +154,7 @@ class _FunctionSepconv(torch.autograd.Function):
     @staticmethod
     def forward(self, input, vertical, horizontal):
         self.save_for_backward(input, vertical, horizontal)
-        return _forward_impl(input, vertical, horizontal, None)
+        return _forward_impl(self, input, vertical, horizontal, None)
 
     @staticmethod
     def backward(self, gradOutput):

@@ -287,3 +287,35 @@ def test_host_buffer_pipeline_matches_device_path():
     only = pkg.sepconv_forward_backward_host(ti, tv, th)          # forward only, pageable memory
     torch.cuda.synchronize()
     assert torch.equal(only, ref_out.cpu())
+
+
+def test_gray_replicated_shortcut():
+    """SSTEM_SEPCONV_GRAY_REPLICATED: identical channel planes (the reference's gray x3 inputs).
+    Forward bit-identical to the general path; tap gradients within tolerance of fp64."""
+    pkg = _ops()
+    r = np.random.default_rng(5)
+    B, H, W = 2, 21, 45
+    plane = r.random((B, 1, H + 50, W + 50), dtype=np.float32)
+    inp = np.repeat(plane, 3, axis=1)
+    _, v, h, g = cases.sepconv_inputs(B, 3, H, W, seed=6, kind="unit")
+    ti, tv, th, tg = _cuda(inp, v, h, g)
+    ref_out, _, ref_gv, ref_gh = _bwd(ti, tv, th, tg, need_input=False)
+    for mode in ("assert", "detect"):
+        pkg.set_gray_replicated(mode)
+        try:
+            out, _, gv, gh = _bwd(ti, tv, th, tg, need_input=False)
+        finally:
+            pkg.set_gray_replicated("off")
+        assert torch.equal(out, ref_out), mode
+        gv64, gh64 = oracle.sepconv_grad_taps_f64(g, inp, v, h)
+        _check_p(gv.cpu().numpy(), oracle.sepconv_grad_vertical_reforder(g, inp, h), gv64, "gray gv " + mode)
+        _check_p(gh.cpu().numpy(), oracle.sepconv_grad_horizontal_reforder(g, inp, v), gh64, "gray gh " + mode)
+    # detection must NOT fire on planes that differ
+    inp2 = inp.copy(); inp2[0, 1, 3, 3] += 0.5
+    t2 = torch.from_numpy(inp2).cuda()
+    pkg.set_gray_replicated("detect")
+    try:
+        out2 = pkg.SeparableConvolution.apply(t2, tv, th)
+    finally:
+        pkg.set_gray_replicated("off")
+    assert torch.equal(out2, pkg.SeparableConvolution.apply(t2, tv, th))

@@ -53,6 +53,15 @@ def main():
             print(json.dumps({"op": "bwd_taps", "shape": [B, C, H, W], "ms": round(ms, 4), "gpix_s": round(px / ms / 1e6, 3),
                               "tflops_alg": round(fl / ms / 1e9, 2), "frac_probe": round(fl / ms / 1e9 / peak, 3)}))
             del gv, gh
+        if "gray" in what and C == 3:
+            gv, gh = torch.empty_like(v), torch.empty_like(h)
+            inp[:, 1:] = inp[:, :1]
+            ms_f = timeit(lambda: lib.sstem_sepconv_forward(inp.data_ptr(), v.data_ptr(), h.data_ptr(), out.data_ptr(), B, C, H, W, K, 2, st))
+            ms_b = timeit(lambda: lib.sstem_sepconv_backward(g.data_ptr(), inp.data_ptr(), v.data_ptr(), h.data_ptr(), None, gv.data_ptr(), gh.data_ptr(), B, C, H, W, K, 2, st), reps=3, warm=1)
+            print(json.dumps({"op": "gray_x3 fwd / bwd_taps", "shape": [B, C, H, W], "ms_fwd": round(ms_f, 4), "ms_bwd": round(ms_b, 4),
+                              "fwd_gpix_s": round(px / ms_f / 1e6, 3), "bwd_gpix_s": round(px / ms_b / 1e6, 3),
+                              "fwd_tapGBs": round(px * 408 / ms_f / 1e6, 1), "bwd_GBs": round(px * 840 / ms_b / 1e6, 1)}))
+            del gv, gh
         if "gi" in what:
             gi = torch.empty_like(inp)
             ms = timeit(lambda: lib.sstem_sepconv_backward(g.data_ptr(), inp.data_ptr(), v.data_ptr(), h.data_ptr(), gi.data_ptr(), None, None, B, C, H, W, K, 0, st), reps=2, warm=1)
