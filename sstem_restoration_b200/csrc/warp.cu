@@ -377,53 +377,95 @@ static int try_launch_warp_tma(const float* moving, const float* flow, const int
 }
 
 // ---- numpy image_warp semantics -------------------------------------------------
-template <typename PixT>
-__device__ __forceinline__ float pix_load(const PixT* p) { return (float)__ldg(p); }
-
-template <typename PixT, bool NEAREST>
+// One thread owns 4 consecutive pixels of the flat [B*H*W] index space: the flow arrives as two
+// 16-byte loads, the uint8 / float results leave as 4-byte (16-byte) words, and the 16*C gathers of
+// the thread are independent.  CT = compile-time channel count (0 = runtime loop).
+template <typename PixT, bool NEAREST, int CT>
 __global__ void __launch_bounds__(256)
 image_warp_kernel(const PixT* __restrict__ im, const float* __restrict__ flow,
                   uint8_t* __restrict__ out_u8, float* __restrict__ out_f32,
                   int C, int H, int W, int64_t total) {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // pixel index over B*H*W
-    if (idx >= total) return;
-    const int j = (int)(idx % W);
-    const int i = (int)((idx / W) % H);
-    const int64_t b = idx / ((int64_t)W * H);
-    const float2 f = __ldcs(reinterpret_cast<const float2*>(flow) + idx);
-    const float ffx = floorf(f.x), ffy = floorf(f.y);
-    // image_warp.py:45-57: integer displacement, then clip (bounded first so the add cannot overflow)
-    const float lim = 1073741824.0f;
-    const int dxi = (int)fminf(fmaxf(ffx, -lim), lim), dyi = (int)fminf(fmaxf(ffy, -lim), lim);
-    const int x0 = min(max(j + dxi, 0), W - 1);
-    const int y0 = min(max(i + dyi, 0), H - 1);
-    const PixT* base = im + b * (int64_t)H * W * C;
-    const int64_t o = idx * C;
-    if (NEAREST) {
-        const PixT* src = base + ((int64_t)y0 * W + x0) * C;
-        for (int c = 0; c < C; ++c) {
-            const float val = pix_load(src + c);
-            if (out_f32) out_f32[o + c] = val;
-            if (out_u8) out_u8[o + c] = (uint8_t)(int)val;
+    constexpr int PX = 4;
+    const int64_t idx0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * PX;   // first pixel of this thread
+    if (idx0 >= total) return;
+    const int nc = CT > 0 ? CT : C;
+    const bool full = idx0 + PX <= total;
+    float fx[PX], fy[PX];
+    if (full) {                                          // 32 bytes of flow, 32-byte aligned
+        const float4 a = __ldcs(reinterpret_cast<const float4*>(flow + 2 * idx0));
+        const float4 c = __ldcs(reinterpret_cast<const float4*>(flow + 2 * idx0) + 1);
+        fx[0] = a.x; fy[0] = a.y; fx[1] = a.z; fy[1] = a.w; fx[2] = c.x; fy[2] = c.y; fx[3] = c.z; fy[3] = c.w;
+    } else {
+#pragma unroll
+        for (int p = 0; p < PX; ++p) {
+            const int64_t q = min(idx0 + p, total - 1);
+            fx[p] = __ldg(flow + 2 * q); fy[p] = __ldg(flow + 2 * q + 1);
         }
-        return;
     }
-    // :84-88 -- x1 is taken from the CLIPPED x0
-    const int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
-    // :72-82 -- weights from frac(flow), independent of clipping
-    const float xw = __fsub_rn(f.x, ffx), yw = __fsub_rn(f.y, ffy);
-    const float ax = __fsub_rn(1.0f, xw), ay = __fsub_rn(1.0f, yw);
-    const float wa = __fmul_rn(ax, ay), wb = __fmul_rn(ax, yw), wc = __fmul_rn(xw, ay), wd = __fmul_rn(xw, yw);
-    const PixT* pa = base + ((int64_t)y0 * W + x0) * C;
-    const PixT* pb = base + ((int64_t)y1 * W + x0) * C;
-    const PixT* pc = base + ((int64_t)y0 * W + x1) * C;
-    const PixT* pd = base + ((int64_t)y1 * W + x1) * C;
-    for (int c = 0; c < C; ++c) {
-        float r = __fadd_rn(__fmul_rn(wa, pix_load(pa + c)), __fmul_rn(wb, pix_load(pb + c)));
-        r = __fadd_rn(r, __fmul_rn(wc, pix_load(pc + c)));
-        r = __fadd_rn(r, __fmul_rn(wd, pix_load(pd + c)));
-        if (out_f32) out_f32[o + c] = r;
-        if (out_u8) out_u8[o + c] = (uint8_t)(int)r;   // :110 astype(uint8): truncation
+    int j = (int)(idx0 % W);
+    int i = (int)((idx0 / W) % H);
+    int64_t b = idx0 / ((int64_t)W * H);
+    int oa[PX], ob[PX], oc[PX], od[PX];                 // pixel offsets (in pixels) of the 4 taps inside image b
+    int64_t boff[PX];
+    float wa[PX], wb[PX], wc[PX], wd[PX];
+#pragma unroll
+    for (int p = 0; p < PX; ++p) {
+        const float ffx = floorf(fx[p]), ffy = floorf(fy[p]);
+        // image_warp.py:45-57: integer displacement, then clip (bounded first so the add cannot overflow)
+        const float lim = 1073741824.0f;
+        const int dxi = (int)fminf(fmaxf(ffx, -lim), lim), dyi = (int)fminf(fmaxf(ffy, -lim), lim);
+        const int x0 = min(max(j + dxi, 0), W - 1);
+        const int y0 = min(max(i + dyi, 0), H - 1);
+        // :84-88 -- x1 is taken from the CLIPPED x0
+        const int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
+        oa[p] = y0 * W + x0; ob[p] = y1 * W + x0; oc[p] = y0 * W + x1; od[p] = y1 * W + x1;
+        boff[p] = b * (int64_t)H * W;
+        // :72-82 -- weights from frac(flow), independent of clipping
+        const float xw = __fsub_rn(fx[p], ffx), yw = __fsub_rn(fy[p], ffy);
+        const float ax = __fsub_rn(1.0f, xw), ay = __fsub_rn(1.0f, yw);
+        wa[p] = __fmul_rn(ax, ay); wb[p] = __fmul_rn(ax, yw); wc[p] = __fmul_rn(xw, ay); wd[p] = __fmul_rn(xw, yw);
+        if (++j == W) { j = 0; if (++i == H) { i = 0; ++b; } }
+    }
+    // results of the 4 pixels, channel-interleaved exactly as they lie in NHWC memory
+    constexpr int MAXV = CT > 0 ? PX * CT : 1;
+    float res[MAXV];
+    auto one = [&](int p, int c) -> float {
+        const PixT* base = im + boff[p] * nc + c;
+        if (NEAREST) return (float)__ldg(base + (int64_t)oa[p] * nc);
+        const float Ia = (float)__ldg(base + (int64_t)oa[p] * nc), Ib = (float)__ldg(base + (int64_t)ob[p] * nc);
+        const float Ic = (float)__ldg(base + (int64_t)oc[p] * nc), Id = (float)__ldg(base + (int64_t)od[p] * nc);
+        float r = __fadd_rn(__fmul_rn(wa[p], Ia), __fmul_rn(wb[p], Ib));
+        r = __fadd_rn(r, __fmul_rn(wc[p], Ic));
+        return __fadd_rn(r, __fmul_rn(wd[p], Id));
+    };
+    if (CT > 0 && full) {
+#pragma unroll
+        for (int p = 0; p < PX; ++p)
+#pragma unroll
+            for (int c = 0; c < CT; ++c) res[p * CT + c] = one(p, c);
+        const int64_t o = idx0 * CT;                     // 4*CT consecutive elements, 4*CT-aligned
+        if (out_f32) {
+#pragma unroll
+            for (int k = 0; k < CT; ++k)
+                __stcs(reinterpret_cast<float4*>(out_f32 + o) + k, make_float4(res[4 * k], res[4 * k + 1], res[4 * k + 2], res[4 * k + 3]));
+        }
+        if (out_u8) {
+#pragma unroll
+            for (int k = 0; k < CT; ++k) {               // :110 astype(uint8): truncation
+                const uchar4 q = make_uchar4((uint8_t)(int)res[4 * k], (uint8_t)(int)res[4 * k + 1],
+                                             (uint8_t)(int)res[4 * k + 2], (uint8_t)(int)res[4 * k + 3]);
+                __stcs(reinterpret_cast<uchar4*>(out_u8 + o) + k, q);
+            }
+        }
+    } else {
+        for (int p = 0; p < PX; ++p) {
+            if (idx0 + p >= total) break;
+            for (int c = 0; c < nc; ++c) {
+                const float r = one(p, c);
+                if (out_f32) out_f32[(idx0 + p) * nc + c] = r;
+                if (out_u8) out_u8[(idx0 + p) * nc + c] = (uint8_t)(int)r;
+            }
+        }
     }
 }
 
@@ -478,16 +520,27 @@ extern "C" int sstem_image_warp(const void* im, int32_t pix_type, const float* f
     DeviceGuard guard(out_u8 ? (const void*)out_u8 : (const void*)out_f32);
     if (guard.err) return guard.err;
     cudaStream_t s = (cudaStream_t)stream;
+    if (H * W > INT32_MAX) return SSTEM_E_SHAPE;       // in-image pixel offsets are 32-bit
     const int64_t total = B * H * W;
-    const unsigned blocks = (unsigned)((total + 255) / 256);
+    const unsigned blocks = (unsigned)(((total + 3) / 4 + 255) / 256);
     const bool nearest = mode == SSTEM_WARP_NEAREST;
-    if (pix_type == SSTEM_PIX_U8) {
-        if (nearest) image_warp_kernel<uint8_t, true><<<blocks, 256, 0, s>>>((const uint8_t*)im, flow, out_u8, out_f32, (int)C, (int)H, (int)W, total);
-        else image_warp_kernel<uint8_t, false><<<blocks, 256, 0, s>>>((const uint8_t*)im, flow, out_u8, out_f32, (int)C, (int)H, (int)W, total);
-    } else {
-        if (nearest) image_warp_kernel<float, true><<<blocks, 256, 0, s>>>((const float*)im, flow, out_u8, out_f32, (int)C, (int)H, (int)W, total);
-        else image_warp_kernel<float, false><<<blocks, 256, 0, s>>>((const float*)im, flow, out_u8, out_f32, (int)C, (int)H, (int)W, total);
+    // the vector stores need 4-byte (uint8) / 16-byte (float) aligned outputs and 16-byte aligned flow
+    const bool vec_ok = aligned16(flow) && (!out_u8 || aligned4(out_u8)) && (!out_f32 || aligned16(out_f32));
+#define SSTEM_IW_LAUNCH(T_, N_, CT_)                                                                              \
+    image_warp_kernel<T_, N_, CT_><<<blocks, 256, 0, s>>>((const T_*)im, flow, out_u8, out_f32, (int)C, (int)H, (int)W, total)
+#define SSTEM_IW_DISPATCH(T_, N_)                                                    \
+    {                                                                                \
+        if (vec_ok && C == 1) SSTEM_IW_LAUNCH(T_, N_, 1);                            \
+        else if (vec_ok && C == 3) SSTEM_IW_LAUNCH(T_, N_, 3);                       \
+        else SSTEM_IW_LAUNCH(T_, N_, 0);                                             \
     }
+    if (pix_type == SSTEM_PIX_U8) {
+        if (nearest) SSTEM_IW_DISPATCH(uint8_t, true) else SSTEM_IW_DISPATCH(uint8_t, false)
+    } else {
+        if (nearest) SSTEM_IW_DISPATCH(float, true) else SSTEM_IW_DISPATCH(float, false)
+    }
+#undef SSTEM_IW_DISPATCH
+#undef SSTEM_IW_LAUNCH
     count_launch();
     return finish_launch();
 }

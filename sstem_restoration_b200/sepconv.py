@@ -102,11 +102,12 @@ def _forward_impl(ctx, input, vertical, horizontal, filter_size):
     if output.numel() == 0:
         return output
     ctx.gray = K == 51 and _is_gray(input)
-    with torch.cuda.device_of(input):
-        code = _lib.load().sstem_sepconv_forward(
-            input.data_ptr(), vertical.data_ptr(), horizontal.data_ptr(), output.data_ptr(),
-            B, C, oh, ow, K, _flags(ctx.gray), _stream_ptr(input))
-    _lib.check(code, "sstem_sepconv_forward")
+    # the library launches on the device that owns `output`; only the stream has to be the caller's
+    code = _lib.load().sstem_sepconv_forward(
+        input.data_ptr(), vertical.data_ptr(), horizontal.data_ptr(), output.data_ptr(),
+        B, C, oh, ow, K, _flags(ctx.gray), _stream_ptr(input))
+    if code:
+        _lib.check(code, "sstem_sepconv_forward")
     return output
 
 
@@ -122,14 +123,14 @@ def _backward_impl(ctx, grad_output):
     grad_vertical = torch.empty_like(vertical) if need_v else None
     grad_horizontal = torch.empty_like(horizontal) if need_h else None
     if (need_in or need_v or need_h) and grad_output.numel() > 0:
-        with torch.cuda.device_of(input):
-            code = _lib.load().sstem_sepconv_backward(
-                grad_output.data_ptr(), input.data_ptr(), vertical.data_ptr(), horizontal.data_ptr(),
-                grad_input.data_ptr() if need_in else None,
-                grad_vertical.data_ptr() if need_v else None,
-                grad_horizontal.data_ptr() if need_h else None,
-                B, C, oh, ow, K, _flags(getattr(ctx, "gray", False)), _stream_ptr(input))
-        _lib.check(code, "sstem_sepconv_backward")
+        code = _lib.load().sstem_sepconv_backward(
+            grad_output.data_ptr(), input.data_ptr(), vertical.data_ptr(), horizontal.data_ptr(),
+            grad_input.data_ptr() if need_in else None,
+            grad_vertical.data_ptr() if need_v else None,
+            grad_horizontal.data_ptr() if need_h else None,
+            B, C, oh, ow, K, _flags(getattr(ctx, "gray", False)), _stream_ptr(input))
+        if code:
+            _lib.check(code, "sstem_sepconv_backward")
     return grad_input, grad_vertical, grad_horizontal
 
 

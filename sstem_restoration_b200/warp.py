@@ -33,23 +33,31 @@ def _require_cuda():
         raise _lib.SstemError("sstem_restoration_b200 warp: no CUDA device; there is no CPU fallback")
 
 
+def _warp_launch(moving, flow, nhwc_memory):
+    """moving [B,C,H,W] CUDA float32 contiguous, flow [B,H,W,2] CUDA float32 (any strides)."""
+    B, C, H, W = moving.shape
+    if nhwc_memory:
+        out = torch.empty((B, H, W, C), dtype=torch.float32, device=moving.device)
+    else:
+        out = torch.empty((B, C, H, W), dtype=torch.float32, device=moving.device)
+    if out.numel() == 0:
+        return out.permute(0, 3, 1, 2) if nhwc_memory else out
+    strides = (ctypes.c_int64 * 4)(*flow.stride())
+    # the library launches on the device that owns `out`; only the stream has to be the caller's
+    code = _lib.load().sstem_warp_forward(
+        moving.data_ptr(), flow.data_ptr(), strides, out.data_ptr(), B, C, H, W,
+        _lib.LAYOUT_NHWC if nhwc_memory else _lib.LAYOUT_NCHW, _stream_ptr(moving.device))
+    if code:
+        _lib.check(code, "sstem_warp_forward")
+    return out.permute(0, 3, 1, 2) if nhwc_memory else out
+
+
 class _WarpFunction(torch.autograd.Function):
+    """Only used when a gradient could be requested: its backward explains why there is none."""
+
     @staticmethod
     def forward(ctx, moving, flow, nhwc_memory):
-        B, C, H, W = moving.shape
-        if nhwc_memory:
-            out = torch.empty((B, H, W, C), dtype=torch.float32, device=moving.device)
-        else:
-            out = torch.empty((B, C, H, W), dtype=torch.float32, device=moving.device)
-        if out.numel() == 0:
-            return out.permute(0, 3, 1, 2) if nhwc_memory else out
-        strides = (ctypes.c_int64 * 4)(*flow.stride())
-        with torch.cuda.device_of(moving):
-            code = _lib.load().sstem_warp_forward(
-                moving.data_ptr(), flow.data_ptr(), strides, out.data_ptr(), B, C, H, W,
-                _lib.LAYOUT_NHWC if nhwc_memory else _lib.LAYOUT_NCHW, _stream_ptr(moving.device))
-        _lib.check(code, "sstem_warp_forward")
-        return out.permute(0, 3, 1, 2) if nhwc_memory else out
+        return _warp_launch(moving, flow, nhwc_memory)
 
     @staticmethod
     def backward(ctx, grad):
@@ -81,10 +89,17 @@ class SpatialTransformation(nn.Module):
         if tuple(deformation_matrix.shape[:3]) != (B, H, W):
             raise ValueError("deformation_matrix must be [B,H,W,2] matching moving_image")
         host = not moving_image.is_cuda
-        dev = torch.device("cuda", torch.cuda.current_device()) if host else moving_image.device
-        moving = moving_image.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
-        flow = deformation_matrix.to(device=dev, dtype=torch.float32, non_blocking=True)  # strides kept
-        out = _WarpFunction.apply(moving, flow, self.nhwc_memory)
+        if host or moving_image.dtype != torch.float32 or deformation_matrix.dtype != torch.float32 \
+                or deformation_matrix.device != moving_image.device:
+            dev = torch.device("cuda", torch.cuda.current_device()) if host else moving_image.device
+            moving_image = moving_image.to(device=dev, dtype=torch.float32, non_blocking=True)
+            deformation_matrix = deformation_matrix.to(device=dev, dtype=torch.float32, non_blocking=True)  # strides kept
+        if not moving_image.is_contiguous():
+            moving_image = moving_image.contiguous()
+        if torch.is_grad_enabled() and (moving_image.requires_grad or deformation_matrix.requires_grad):
+            out = _WarpFunction.apply(moving_image, deformation_matrix, self.nhwc_memory)
+        else:
+            out = _warp_launch(moving_image, deformation_matrix, self.nhwc_memory)
         return out.cpu() if host else out
 
 
@@ -139,12 +154,12 @@ def _image_warp_cuda(im_t, flow_t, mode="bilinear", want_float=False, want_u8=Tr
     out_u8 = torch.empty((B, H, W, C), dtype=torch.uint8, device=im4.device) if want_u8 else None
     out_f = torch.empty((B, H, W, C), dtype=torch.float32, device=im4.device) if want_float else None
     if im4.numel() > 0:
-        with torch.cuda.device_of(im4):
-            code = _lib.load().sstem_image_warp(
-                im4.data_ptr(), _lib.PIX_U8 if im4.dtype == torch.uint8 else _lib.PIX_F32, fl4.data_ptr(),
-                out_u8.data_ptr() if want_u8 else None, out_f.data_ptr() if want_float else None,
-                B, H, W, C, m, _stream_ptr(im4.device))
-        _lib.check(code, "sstem_image_warp")
+        code = _lib.load().sstem_image_warp(
+            im4.data_ptr(), _lib.PIX_U8 if im4.dtype == torch.uint8 else _lib.PIX_F32, fl4.data_ptr(),
+            out_u8.data_ptr() if want_u8 else None, out_f.data_ptr() if want_float else None,
+            B, H, W, C, m, _stream_ptr(im4.device))
+        if code:
+            _lib.check(code, "sstem_image_warp")
 
     def _shape(t):
         if t is None:

@@ -319,3 +319,32 @@ def test_gray_replicated_shortcut():
     finally:
         pkg.set_gray_replicated("off")
     assert torch.equal(out2, pkg.SeparableConvolution.apply(t2, tv, th))
+
+
+def test_window_rows_outside_a_pixels_support_cannot_leak_nan():
+    """The tuned kernels walk 58 input rows per 8-row tile; a row below a pixel's own 51-row window
+    is multiplied by a zero weight internally.  A NaN / Inf there must not reach that pixel."""
+    pkg = _ops()
+    inp, v, h, g = cases.sepconv_inputs(1, 3, 8, 40, seed=12, kind="unit")
+    ref = _fwd(*_cuda(inp, v, h)).cpu().numpy()
+    bad = inp.copy()
+    bad[:, :, 57, :] = np.nan            # last input row: only output row 7 may see it
+    bad[:, :, 56, 5] = np.inf            # row 56: only output rows 6, 7
+    got = _fwd(*_cuda(bad, v, h)).cpu().numpy()
+    assert np.array_equal(got[:, :, :6], ref[:, :, :6])          # rows 0..5 untouched, bit for bit
+    assert np.isnan(got[:, :, 7]).all()
+    out, gi, gv, gh = _bwd(*_cuda(bad, v, h, g), need_input=False)
+    assert torch.isfinite(gv[:, :, :6]).all() and torch.isfinite(gh[:, :, :6]).all()
+
+
+def test_operator_runs_on_a_non_current_device_stream_pair():
+    """Replica-thread pattern (nn.DataParallel): tensors decide the device, not the caller's context."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    pkg = _ops()
+    inp, v, h, g = cases.sepconv_inputs(1, 3, 16, 16, seed=13, kind="unit")
+    ref = _fwd(*_cuda(inp, v, h)).cpu()
+    t = [torch.from_numpy(a).to("cuda:1") for a in (inp, v, h)]
+    assert torch.cuda.current_device() == 0
+    out = pkg.SeparableConvolution.apply(*t)
+    assert out.device.index == 1 and torch.equal(out.cpu(), ref)
