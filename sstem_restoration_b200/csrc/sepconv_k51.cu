@@ -377,6 +377,32 @@ __device__ __forceinline__ void bwd_step(const float* __restrict__ prow0, bool n
                                          float2 (&gvp)[R / 2]) {
     using Gm = Geo<G, R>;
     constexpr int NP = Gm::NP, NT = Gm::NT;
+    if (CC == 1) {
+        // One channel (also the gray x3 shortcut): t = g * P, so g factors out of both sums --
+        //   gv[fy] = g * sum_fx P h[fx],   gh[fx] = g * sum_fy P v[fy]
+        // 2 FMAs per (fy, fx) instead of 3; the caller multiplies by g (gv per step, gh once per tile).
+#pragma unroll
+        for (int pp = 0; pp < NP; ++pp) gvp[pp] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            float P = prow0[G * t];
+            if (t == NT - 1) P = novalid ? 0.f : P;
+#pragma unroll
+            for (int pp = 0; pp < NP; ++pp) {
+                float2 P2 = make_float2(P, P);
+                if (S >= 0) {                            // a row whose fy is out of range must not see P
+                    if (S < 2 * pp || S > 2 * pp + K51) continue;
+                    if (S - 2 * pp > K51 - 1) P2.x = 0.f;
+                    if (S - 2 * pp - 1 < 0) P2.y = 0.f;
+                }
+                if (WV) gvp[pp] = __ffma2_rn(P2, h2[pp][t], gvp[pp]);
+                if (WH) gh2[pp][t] = __ffma2_rn(P2, v2[pp], gh2[pp][t]);
+            }
+        }
+#pragma unroll
+        for (int pp = 0; pp < NP; ++pp) gvp[pp] = __fmul2_rn(gvp[pp], g2[0][pp]);
+        return;
+    }
     constexpr int TB = (NT + 1) / 2;                     // taps per block: NP*TB independent FFMA2 chains
     float2 gva[NP], gvb[NP];                             // two partial sums per row pair
 #pragma unroll
@@ -550,8 +576,9 @@ sepconv_bwd_taps_k51_kernel(const float* __restrict__ gout, const float* __restr
                 const int ya = y0 + 2 * pp, yb = ya + 1;
                 float* da = gp + (int64_t)(G * t) * plane + (int64_t)ya * W;
                 float* db = gp + (int64_t)(G * t) * plane + (int64_t)yb * W;
-                if (ya < H) *da = accumulate ? (*da + gh2[pp][t].x) : gh2[pp][t].x;
-                if (yb < H) *db = accumulate ? (*db + gh2[pp][t].y) : gh2[pp][t].y;
+                const float2 val = (CC == 1) ? __fmul2_rn(gh2[pp][t], g2[0][pp]) : gh2[pp][t];   // CC == 1: g was factored out
+                if (ya < H) *da = accumulate ? (*da + val.x) : val.x;
+                if (yb < H) *db = accumulate ? (*db + val.y) : val.y;
             }
         }
     }

@@ -34,11 +34,14 @@ def max_units_per_rank(n_units: int, world_size: int) -> int:
     return -(-n_units // world_size)
 
 
-def gather_sections(local: torch.Tensor, n_units: int, group=None) -> torch.Tensor:
-    """All-gather the per-rank outputs [n_local, ...] into [n_units, ...] in unit order.
+def gather_sections(local: torch.Tensor, n_units: int, group=None, dst=None):
+    """Gather the per-rank outputs [n_local, ...] into [n_units, ...] in unit order.
 
+    ``dst=None``: every rank gets the result (one all_gather_into_tensor).  ``dst=r``: only rank
+    ``r`` does (what nn.DataParallel's output gather does in the reference, main_ms.py:97-103);
+    the other ranks return None -- 1/world_size of the traffic.
     Ranks may hold different counts (n_units % world_size != 0): each rank pads to
-    the maximum, one all_gather_into_tensor moves the data, padding is dropped.
+    the maximum, padding is dropped on arrival.
     """
     if not (dist.is_available() and dist.is_initialized()):
         return local
@@ -52,8 +55,17 @@ def gather_sections(local: torch.Tensor, n_units: int, group=None) -> torch.Tens
     if local.shape[0] < m:
         pad = torch.zeros((m - local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
         padded = torch.cat([local, pad], 0)
-    out = torch.empty((ws * m,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(out, padded.contiguous(), group=group)
+    if dst is not None:
+        bufs = None
+        if rank == dst:
+            bufs = [torch.empty_like(padded) for _ in range(ws)]
+        dist.gather(padded.contiguous(), bufs, dst=dst, group=group)
+        if rank != dst:
+            return None
+        out = torch.cat(bufs, 0)
+    else:
+        out = torch.empty((ws * m,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, padded.contiguous(), group=group)
     pieces = []
     for r in range(ws):
         rlo, rhi = shard_range(n_units, r, ws)

@@ -25,6 +25,12 @@ def _worker(rank, world, port, n_units, q):
     local = torch.stack([torch.full((2, 3), float(k)) for k in range(lo, hi)]) if hi > lo else torch.zeros((0, 2, 3))
     full = shard.gather_sections(local, n_units)
     ok = full.shape == (n_units, 2, 3) and all(bool((full[k] == k).all()) for k in range(n_units))
+    # gather to one rank only (the DataParallel pattern): rank 1 receives, rank 0 gets None
+    one = shard.gather_sections(local, n_units, dst=1)
+    if rank == 1:
+        ok = ok and one.shape == (n_units, 2, 3) and all(bool((one[k] == k).all()) for k in range(n_units))
+    else:
+        ok = ok and one is None
     # timing reduction used by bench.py: max over ranks
     t = torch.tensor([float(rank + 1)])
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
