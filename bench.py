@@ -354,8 +354,9 @@ def run_gpu_arm(args):
     dominant = "sepconv_bwd_taps" if bwd_ms >= fwd_ms else "sepconv_fwd"
     roof = dict(rooflines[dominant])
     roof["kernel"] = dominant
-    roof["peak_source"] = (f"FFMA probe on this GPU in this run (sstem_fp32_peak_probe, {probe_mhz:.0f} MHz seen); nominal "
-                           "148 SM x 128 lanes x 2 x 1.965 GHz = 74.4 TFLOP/s; MEASURED_PEAKS.json has no fp32 row")
+    roof["peak_source"] = ("FFMA probe on this GPU in this run (sstem_fp32_peak_probe: best of 3 register-resident FMA loops; SM "
+                           "clocks in `clocks`); nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4 TFLOP/s; MEASURED_PEAKS.json has "
+                           "no fp32 row")
 
     cpu_val, cpu_dt, cpu_sample = cpu_sepconv_sample(steps=3, warmup=1)
     line = {

@@ -107,11 +107,10 @@ extern "C" int sstem_fp32_peak_probe(double* tflops_out, double* sm_mhz_out) {
         unsigned long long hc = 0;
         cudaMemcpy(&hc, cyc, sizeof(hc), cudaMemcpyDeviceToHost);
         const double tflops = 2.0 * fma_per_thread * blocks * threads / (best_ms * 1e-3) / 1e12;
-        if (tflops > best_tflops) {
-            best_tflops = tflops;
-            // all CTAs are co-resident (one wave): one CTA's loop spans the kernel, cycles / time = clock
-            best_mhz = (double)hc / (best_ms * 1e-3) / 1e6;
-        }
+        if (tflops > best_tflops) best_tflops = tflops;
+        // variant 0 (44 registers) runs as ONE wave of co-resident CTAs: its loop spans the kernel, so
+        // cycles / time = the SM clock under this load
+        if (variant == 0) best_mhz = (double)hc / (best_ms * 1e-3) / 1e6;
     }
     e = cudaGetLastError();
     *tflops_out = best_tflops;

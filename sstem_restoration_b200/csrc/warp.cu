@@ -176,6 +176,7 @@ warp_torch_kernel(const float* __restrict__ moving, const float* __restrict__ fl
 constexpr int WT_TH = SSTEM_WARP_TH, WT_TW = 64;      // output tile; WT_TH * 16 threads, 4 pixels each
 constexpr int WT_BH = SSTEM_WARP_BH, WT_BW = 96;      // source window (box of the image tensor map)
 constexpr int WT_SH = WT_TH + 4, WT_SW = 72;          // small window, tried first (smooth flows): 1.7x the tile
+constexpr int WT_MH = WT_TH + 8, WT_MW = 80;          // medium window: 2.5x the tile
 constexpr int WT_THREADS = WT_TH * 16;
 constexpr int WT_HALF = WT_TH / 2;                    // a thread's two rows are WT_HALF apart
 
@@ -209,7 +210,7 @@ template <int CT>
 __global__ void __launch_bounds__(WT_THREADS, SSTEM_WARP_TMA_MINB)
 warp_torch_tma_kernel(const __grid_constant__ CUtensorMap map_fx, const __grid_constant__ CUtensorMap map_fy,
                       const __grid_constant__ CUtensorMap map_im, const __grid_constant__ CUtensorMap map_im_small,
-                      const float* __restrict__ moving,
+                      const __grid_constant__ CUtensorMap map_im_mid, const float* __restrict__ moving,
                       float* __restrict__ out, int H, int W) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* s_im = reinterpret_cast<float*>(smem_raw);                       // [CT][BH][BW]
@@ -266,12 +267,13 @@ warp_torch_tma_kernel(const __grid_constant__ CUtensorMap map_fx, const __grid_c
     // the box must start on a 16-byte boundary in global memory: round the left edge down to 4 floats
     const int bx0 = s_box[0] & ~3, by0 = s_box[1], bx1 = s_box[2], by1 = s_box[3];
     const bool small = (bx1 - bx0 < WT_SW) && (by1 - by0 < WT_SH);
-    const bool fits = small || ((bx1 - bx0 < WT_BW) && (by1 - by0 < WT_BH));
-    const int pitch = small ? WT_SW : WT_BW;            // block-uniform
-    const int cstride = small ? WT_SH * WT_SW : WT_BH * WT_BW;
+    const bool mid = !small && (bx1 - bx0 < WT_MW) && (by1 - by0 < WT_MH);
+    const bool fits = small || mid || ((bx1 - bx0 < WT_BW) && (by1 - by0 < WT_BH));
+    const int pitch = small ? WT_SW : (mid ? WT_MW : WT_BW);            // block-uniform
+    const int cstride = small ? WT_SH * WT_SW : (mid ? WT_MH * WT_MW : WT_BH * WT_BW);
     if (fits && tid == 0) {
         mbar_expect_tx(&bar[1], (unsigned)(CT * cstride * sizeof(float)));
-        tma_load_3d(s_im, small ? &map_im_small : &map_im, &bar[1], bx0, by0, b * CT);
+        tma_load_3d(s_im, small ? &map_im_small : (mid ? &map_im_mid : &map_im), &bar[1], bx0, by0, b * CT);
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) offa[q] = (ya[q] - by0) * pitch + (xa[q] - bx0);
@@ -356,11 +358,12 @@ static int try_launch_warp_tma(const float* moving, const float* flow, const int
                                int64_t B, int64_t H, int64_t W, cudaStream_t s) {
     if ((W & 3) || fs[2] != 1 || !aligned16(moving) || !aligned16(flow) || !aligned16(out)) return -1000;
     if ((fs[0] & 3) || (fs[1] & 3) || (fs[3] & 3) || fs[1] < W || B > 65535 || (H + WT_TH - 1) / WT_TH > 65535) return -1000;
-    CUtensorMap mfx, mfy, mim, mims;
+    CUtensorMap mfx, mfy, mim, mims, mimm;
     if (!make_map3(&mfx, flow, W, H, B, fs[1], fs[0], WT_TW, WT_TH, 1)) return -1000;
     if (!make_map3(&mfy, flow + fs[3], W, H, B, fs[1], fs[0], WT_TW, WT_TH, 1)) return -1000;
     if (!make_map3(&mim, moving, W, H, B * CT, W, H * W, WT_BW, WT_BH, CT)) return -1000;
     if (!make_map3(&mims, moving, W, H, B * CT, W, H * W, WT_SW, WT_SH, CT)) return -1000;
+    if (!make_map3(&mimm, moving, W, H, B * CT, W, H * W, WT_MW, WT_MH, CT)) return -1000;
     const size_t smem = (size_t)(CT * WT_BH * WT_BW + 2 * WT_TH * WT_TW) * sizeof(float) + 64;
     static bool done[16] = {};
     int dev = 0;
@@ -371,7 +374,7 @@ static int try_launch_warp_tma(const float* moving, const float* flow, const int
         done[dev & 15] = true;
     }
     dim3 grid((unsigned)((W + WT_TW - 1) / WT_TW), (unsigned)((H + WT_TH - 1) / WT_TH), (unsigned)B);
-    warp_torch_tma_kernel<CT><<<grid, WT_THREADS, smem, s>>>(mfx, mfy, mim, mims, moving, out, (int)H, (int)W);
+    warp_torch_tma_kernel<CT><<<grid, WT_THREADS, smem, s>>>(mfx, mfy, mim, mims, mimm, moving, out, (int)H, (int)W);
     count_launch();
     return finish_launch();
 }

@@ -1,0 +1,94 @@
+"""BASELINE config 5 in miniature: restore a synthetic EM stack, sharded by section pair.
+
+    python tools/stack_restore.py --sections 20 --size 2048            # 1 GPU
+    torchrun --nproc-per-node 8 tools/stack_restore.py --sections 100 --size 4096
+
+Target k (interior section) is interpolated from sections k-1 and k+1 exactly as the reference's
+tail does (sff_scripts_interp/inference.py:69-89 -> model_interp.py:90-97): two sepconv calls on the
+replicate-padded neighbours + add + channel mean; the degraded section k itself is flow-warped
+(sff_scripts_fusion/inference.py:149-150).  Taps and flows are synthetic (the KPN / flow net are out
+of scope).  Ranks own contiguous target ranges (shard.shard_range), never communicate while
+computing, and the restored sections are gathered to rank 0 at the end (the path's only collective).
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import sstem_restoration_b200 as pkg  # noqa: E402
+from sstem_restoration_b200 import shard, synth  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--sections", type=int, default=20)
+    ap.add_argument("--size", type=int, default=2048)
+    ap.add_argument("--gray", default="detect", choices=["off", "assert", "detect"])
+    args = ap.parse_args()
+    rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        dist.init_process_group("nccl", device_id=dev)
+    H = W = args.size
+    targets = shard.stack_targets(args.sections)
+    lo, hi = shard.shard_range(len(targets), rank, world)
+    pkg.set_gray_replicated(args.gray)
+    sep = pkg.SeparableConvolution.apply
+    warp = pkg.SpatialTransformation(True)
+    gen = torch.Generator(device=dev).manual_seed(4321 + rank)
+    # synthetic taps / flow, reused for every pair (their values do not affect speed)
+    taps = [torch.softmax(torch.randn((1, 51, H, W), device=dev, generator=gen), 1) for _ in range(4)]
+    flow_np, _ = synth.random_fold_flow(H, W, 555)
+    flow = torch.from_numpy(np.ascontiguousarray(flow_np.transpose(2, 0, 1))[None]).to(dev).permute(0, 2, 3, 1)
+    base = torch.from_numpy(synth.section_to_input(synth.em_section(min(H, 1024), min(W, 1024), 0))).to(dev)
+
+    def section(idx):                                   # a cheap deterministic stand-in for PNG decode
+        reps = (1, (H + 50 + base.shape[1] - 1) // base.shape[1], (W + 50 + base.shape[2] - 1) // base.shape[2])
+        return (base.repeat(*reps)[:, : H + 50, : W + 50].roll(idx * 7, 2)[None]).contiguous()
+
+    restored = torch.empty((hi - lo, 1, H, W), device=dev)
+    with torch.no_grad():                               # warm-up: first-launch setup, allocator, NCCL communicator
+        i1 = section(0)
+        _ = torch.mean(sep(i1, taps[0], taps[1]) + sep(i1, taps[2], taps[3]), dim=1, keepdim=True)
+        _ = warp(i1[:, :, 25:-25, 25:-25].contiguous(), flow)
+        if world > 1:
+            shard.gather_sections(torch.zeros((1, 1, 8, 8), device=dev).expand(shard.shard_range(world, rank, world)[1] - shard.shard_range(world, rank, world)[0], 1, 8, 8).contiguous(), world, dst=0)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0 = pkg.launch_count()
+    e0.record()
+    with torch.no_grad():
+        for n, (ka, k, kb) in enumerate(targets[lo:hi]):
+            i1, i2, ik = section(ka), section(kb), section(k)
+            y = sep(i2, taps[0], taps[1]) + sep(i1, taps[2], taps[3])
+            interp = torch.mean(y, dim=1, keepdim=True)
+            warped = warp(ik[:, :, 25:-25, 25:-25].contiguous(), flow)          # correction-module warp of section k
+            restored[n] = 0.5 * (interp[0] + warped[0, :1])
+    full = shard.gather_sections(restored, len(targets), dst=0) if world > 1 else restored
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        t = float(ms.item()) * 1e-3
+        print(json.dumps({"workload": f"stack restoration, {args.sections} sections {H}x{W}, {len(targets)} targets", "n_gpus": world,
+                          "seconds": round(t, 4), "sections_per_s": round(len(targets) / t, 2),
+                          "mpix_per_s": round(len(targets) * H * W / t / 1e6, 1), "gray_mode": args.gray,
+                          "gathered": list(full.shape), "kernel_launches_rank0": pkg.launch_count() - n0}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
