@@ -478,12 +478,13 @@ __device__ __forceinline__ void bwd_step(const float* __restrict__ prow0, bool n
     }
 }
 
-template <int CC, int G, int R, bool VEC, bool PAIR, bool WV, bool WH>
+template <int CC, int G, int R, bool VEC, bool PAIR, bool WV, bool WH, bool ACCUM>
 __global__ void __launch_bounds__(128, 2)
 sepconv_bwd_taps_k51_kernel(const float* __restrict__ gout, const float* __restrict__ in,
                             const float* __restrict__ v, const float* __restrict__ h,
                             float* __restrict__ gv, float* __restrict__ gh,
-                            int C, int c0, int H, int W, int accumulate, int replicas) {
+                            int C, int c0, int H, int W, int replicas) {
+    constexpr bool accumulate = ACCUM;                   // later channel chunks (C > 3) add into gv / gh
     using Gm = Geo<G, R>;
     constexpr int NP = Gm::NP, NT = Gm::NT;
     static_assert(R == G, "the per-step gv reduce maps row p to lane g == p");
@@ -834,10 +835,17 @@ int launch_bwd_variant(const float* g, const float* in, const float* v, const fl
     constexpr int G = SSTEM_BWD_G, R = SSTEM_BWD_R;
     constexpr size_t smem = smem_bytes<G, R, CC>();
     static bool done[16] = {};
-    auto kern = sepconv_bwd_taps_k51_kernel<CC, G, R, VEC, PAIR, WV, WH>;
-    if (int e = set_smem_once(kern, smem, done)) return e;
     dim3 grid((unsigned)((W + Geo<G, R>::TILE_W - 1) / Geo<G, R>::TILE_W), (unsigned)((H + R - 1) / R), (unsigned)B);
-    kern<<<grid, 128, smem, s>>>(g, in, v, h, gv, gh, C, c0, H, W, accumulate, replicas);
+    if (accumulate) {
+        static bool done_a[16] = {};
+        auto kern = sepconv_bwd_taps_k51_kernel<CC, G, R, VEC, PAIR, WV, WH, true>;
+        if (int e = set_smem_once(kern, smem, done_a)) return e;
+        kern<<<grid, 128, smem, s>>>(g, in, v, h, gv, gh, C, c0, H, W, replicas);
+    } else {
+        auto kern = sepconv_bwd_taps_k51_kernel<CC, G, R, VEC, PAIR, WV, WH, false>;
+        if (int e = set_smem_once(kern, smem, done)) return e;
+        kern<<<grid, 128, smem, s>>>(g, in, v, h, gv, gh, C, c0, H, W, replicas);
+    }
     count_launch();
     return finish_launch();
 }
