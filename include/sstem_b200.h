@@ -93,6 +93,52 @@ int sstem_sepconv_backward(const float* grad_output, const float* input,
                            int64_t batch, int64_t channels, int64_t out_h, int64_t out_w,
                            int32_t taps, uint32_t flags, void* stream);
 
+/*
+ * Fused interpolation tail of the kernel-prediction network -- the expression every IFNet
+ * evaluates after its tap branches (sff_scripts_interp/model/model_interp.py:90-97;
+ * sp_scripts_train/networks.py:116-123 evaluates it twice):
+ *
+ *   y      = sepconv(ReplicationPad2d(25)(frame2), k2_vertical, k2_horizontal)
+ *          + sepconv(ReplicationPad2d(25)(frame1), k1_vertical, k1_horizontal)
+ *   output = mean over channels of y                                  -> [batch, 1, h, w]
+ *
+ * Replaces, in one launch, two nn.ReplicationPad2d (model_interp.py:46), two
+ * SeparableConvolution_cuda_forward calls (SeparableConvolution_cuda.h:6-11), the add and
+ * torch.mean(dim=1, keepdim=True) (model_interp.py:94,97).  The padded copies are never
+ * materialised, and because the convolution is linear in the image the channel mean is taken on
+ * the frames, so one plane per frame is convolved instead of `channels`.
+ *   frame1, frame2   [batch, channels, h, w] UNPADDED; planes contiguous, consecutive batches
+ *                    `frame_batch_stride` ELEMENTS apart (the callers pass x[:, :3] / x[:, 3:6]
+ *                    views of one [batch, 6, h, w] tensor: stride 6*h*w)
+ *   k*_vertical / k*_horizontal  [batch, 51, h, w]
+ *   output           [batch, 1, h, w]
+ * taps must be 51.  flags: SSTEM_SEPCONV_GRAY_REPLICATED = the channel planes of each frame are
+ * identical copies (plane 0 is used as is); other flags are rejected.
+ */
+int sstem_interp_tail_forward(const float* frame1, const float* frame2, int64_t frame_batch_stride,
+                              const float* k1_vertical, const float* k1_horizontal,
+                              const float* k2_vertical, const float* k2_horizontal,
+                              float* output,
+                              int64_t batch, int64_t channels, int64_t h, int64_t w,
+                              int32_t taps, uint32_t flags, void* stream);
+
+/*
+ * Tap gradients of sstem_interp_tail_forward given grad_output [batch, 1, h, w] (what autograd
+ * derives from the reference expression: mean -> add -> two SeparableConvolution_cuda_backward
+ * calls, SeparableConvolution_cuda.h:13-21).  Any of the four outputs may be NULL = not wanted;
+ * the frames are data and get no gradient (as in the reference, whose gradInput stays zero --
+ * SeparableConvolution.py:60).
+ *   grad_k*_vertical / grad_k*_horizontal  [batch, 51, h, w]
+ */
+int sstem_interp_tail_backward(const float* grad_output,
+                               const float* frame1, const float* frame2, int64_t frame_batch_stride,
+                               const float* k1_vertical, const float* k1_horizontal,
+                               const float* k2_vertical, const float* k2_horizontal,
+                               float* grad_k1_vertical, float* grad_k1_horizontal,
+                               float* grad_k2_vertical, float* grad_k2_horizontal,
+                               int64_t batch, int64_t channels, int64_t h, int64_t w,
+                               int32_t taps, uint32_t flags, void* stream);
+
 /* memory layout of the warp output */
 #define SSTEM_LAYOUT_NCHW 0
 #define SSTEM_LAYOUT_NHWC 1  /* what the reference materialises (image_warp_torch.py:94,112) */

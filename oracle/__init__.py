@@ -1,7 +1,8 @@
 """ORACLE -- TEST INFRASTRUCTURE ONLY.
 
 CPU restatement of the reference's hot path (sydeng99/ssTEM-restoration):
-the 51-tap adaptive separable local convolution (``libs/sepconv``) and the two
+the 51-tap adaptive separable local convolution (``libs/sepconv``), the expression
+the interpolation network wraps around it (``model_interp.py:90-97``) and the two
 flow-driven bilinear backward warps (``image_warp_torch.SpatialTransformation``
 and numpy ``image_warp``).  Only ``tests/``, ``__graft_entry__.smoke()`` and the
 ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import this
@@ -157,6 +158,40 @@ def sepconv_unfold_torch(inp, v, h):
         term = r * v[:, fy].unsqueeze(1)
         out = term if out is None else out + term
     return out
+
+
+# --------------------------------------------------------------------------- interpolation tail
+def _replicate_pad(x, pad=25):
+    """nn.ReplicationPad2d(pad) (model_interp.py:46) == numpy edge padding of the last two axes."""
+    return np.pad(_f32(x), ((0, 0), (0, 0), (pad, pad), (pad, pad)), mode="edge")
+
+
+def interp_tail_reference(i1, i2, k1v, k1h, k2v, k2h):
+    """The expression IFNet.forward ends with (sff_scripts_interp/model/model_interp.py:90-97),
+    restated from the pinned pieces: replicate-pad both frames, the reference-order sepconv of
+    each (kernel.cu:38-51), frame 2's result + frame 1's, then torch.mean(dim=1, keepdim=True)
+    (fp32 sum over channels divided by C).  -> [B,1,H,W] float32."""
+    y = sepconv_forward_reforder(_replicate_pad(i2), k2v, k2h) + sepconv_forward_reforder(_replicate_pad(i1), k1v, k1h)
+    acc = y[:, 0].copy()
+    for c in range(1, y.shape[1]):
+        acc = acc + y[:, c]
+    return (acc / np.float32(y.shape[1]))[:, None]
+
+
+def interp_tail_f64(i1, i2, k1v, k1h, k2v, k2h):
+    y = sepconv_forward_f64(_replicate_pad(i2), k2v, k2h) + sepconv_forward_f64(_replicate_pad(i1), k1v, k1h)
+    return y.mean(axis=1, keepdims=True)
+
+
+def interp_tail_grads_f64(g, i1, i2, k1v, k1h, k2v, k2h):
+    """fp64 tap gradients of the tail given g [B,1,H,W]: the mean hands g/C to every channel, the
+    add hands it to both sepconvs (kernel.cu:97-111, :134-149 with that upstream gradient).
+    -> (g_k1v, g_k1h, g_k2v, g_k2h)."""
+    C = np.asarray(i1).shape[1]
+    gc = np.repeat(_f32(g) / np.float32(C), C, axis=1)
+    g1v, g1h = sepconv_grad_taps_f64(gc, _replicate_pad(i1), k1v, k1h)
+    g2v, g2h = sepconv_grad_taps_f64(gc, _replicate_pad(i2), k2v, k2h)
+    return g1v, g1h, g2v, g2h
 
 
 # --------------------------------------------------------------------------- warps

@@ -7,6 +7,7 @@ interfaces:
     from sstem_restoration_b200 import SeparableConvolution          # libs/sepconv
     from sstem_restoration_b200 import FunctionSepconv, ModuleSepconv  # model/sepconv.py
     from sstem_restoration_b200 import SpatialTransformation, image_warp
+    from sstem_restoration_b200 import interpolation_tail            # fused IFNet tail (model_interp.py:90-97)
 
 There is no CPU / PyTorch fallback: without libsstem_b200.so (see
 __graft_entry__.build) every operator raises.
@@ -14,6 +15,7 @@ __graft_entry__.build) every operator raises.
 from ._lib import SstemError, launch_count, fp32_peak_probe  # noqa: F401
 from .sepconv import (  # noqa: F401
     SeparableConvolution, FunctionSepconv, ModuleSepconv, set_strict_order, set_gray_replicated,
+    interpolation_tail, ModuleInterpolationTail,
 )
 from .warp import SpatialTransformation, image_warp  # noqa: F401
 from .host import sepconv_forward_backward_host, join_host_pipeline  # noqa: F401
@@ -21,6 +23,7 @@ from . import shard, synth  # noqa: F401
 
 __all__ = [
     "SeparableConvolution", "FunctionSepconv", "ModuleSepconv", "set_strict_order", "set_gray_replicated",
+    "interpolation_tail", "ModuleInterpolationTail",
     "SpatialTransformation", "image_warp", "sepconv_forward_backward_host", "join_host_pipeline", "SstemError", "launch_count", "fp32_peak_probe",
     "shard", "synth",
 ]

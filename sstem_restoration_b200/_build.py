@@ -9,14 +9,31 @@ from __future__ import annotations
 import os
 import shutil
 import subprocess
+import tempfile
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libsstem_b200.so")
-SOURCES = ["abi.cu", "sepconv_generic.cu", "sepconv_k51.cu", "warp.cu", "probe.cu"]
+# (source, extra defines, object suffix).  The tuned sepconv kernels are ~130 template
+# instantiations; they are spread over several translation units (and the tap-gradient file
+# is compiled four times, one -DSSTEM_BWD_PART each) so that a build is parallel.
+UNITS = [
+    ("abi.cu", [], ""),
+    ("sepconv_generic.cu", [], ""),
+    ("sepconv_k51_fwd.cu", [], ""),
+    ("sepconv_k51_bwd.cu", ["-DSSTEM_BWD_PART=0"], "_p0"),
+    ("sepconv_k51_bwd.cu", ["-DSSTEM_BWD_PART=1"], "_p1"),
+    ("sepconv_k51_bwd.cu", ["-DSSTEM_BWD_PART=2"], "_p2"),
+    ("sepconv_k51_bwd.cu", ["-DSSTEM_BWD_PART=3"], "_p3"),
+    ("sepconv_k51_gi.cu", [], ""),
+    ("sepconv_k51_tail.cu", [], ""),
+    ("warp.cu", [], ""),
+    # ("sff_sim.cu", [], ""),
+    ("probe.cu", [], ""),
+]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "-shared", "-Xcompiler", "-fPIC", "--use_fast_math=false", "-Xptxas", "-v",
+    "-Xcompiler", "-fPIC", "-Xptxas", "-v",
 ]
 
 
@@ -27,29 +44,54 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: libsstem_b200.so cannot be built")
 
 
-def needs_build() -> bool:
-    if not os.path.exists(LIB_PATH):
+def needs_build(lib_path: str = LIB_PATH) -> bool:
+    if not os.path.exists(lib_path):
         return True
-    t = os.path.getmtime(LIB_PATH)
+    t = os.path.getmtime(lib_path)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
     deps.append(os.path.join(HERE, "..", "include", "sstem_b200.h"))
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every CUDA source into one shared library; returns its path."""
-    if not force and not needs_build():
-        return LIB_PATH
-    cmd = [_nvcc()] + [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + ["-o", LIB_PATH + ".tmp"]
-    cmd += os.environ.get("SSTEM_NVCC_EXTRA", "").split()        # experiments only, e.g. -DSSTEM_BWD_ROWS=6
-    cmd += [os.path.join(CSRC, s) for s in SOURCES]
-    proc = subprocess.run(cmd, capture_output=True, text=True)
-    log = proc.stdout + proc.stderr
-    with open(os.path.join(HERE, "build.log"), "w") as f:
-        f.write(" ".join(cmd) + "\n" + log)
-    if proc.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + log[-4000:])
-    os.replace(LIB_PATH + ".tmp", LIB_PATH)
+def build(force: bool = False, verbose: bool = False, lib_path: str = LIB_PATH, extra=None) -> str:
+    """Compile every CUDA source (in parallel) and link one shared library; returns its path.
+
+    `extra` / $SSTEM_NVCC_EXTRA: additional nvcc flags for kernel-tuning experiments
+    (e.g. -DSSTEM_BWD_NPRE=5), normally together with another `lib_path`."""
+    if not force and not needs_build(lib_path):
+        return lib_path
+    from concurrent.futures import ThreadPoolExecutor
+
+    nvcc = _nvcc()
+    extra = list(extra or []) + os.environ.get("SSTEM_NVCC_EXTRA", "").split()
+    objdir = tempfile.mkdtemp(prefix="sstem_obj_")
+
+    def compile_one(unit):
+        src, defs, suffix = unit
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + suffix + ".o")
+        cmd = [nvcc] + NVCC_FLAGS + defs + extra + ["-c", os.path.join(CSRC, src), "-o", obj]
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        return obj, " ".join(cmd) + "\n" + proc.stdout + proc.stderr, proc.returncode
+
+    try:
+        with ThreadPoolExecutor(max_workers=min(len(UNITS), os.cpu_count() or 4)) as pool:
+            results = list(pool.map(compile_one, UNITS))
+        log = "".join(r[1] for r in results)
+        failed = [r for r in results if r[2] != 0]
+        if not failed:
+            cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib_path + ".tmp"] + [r[0] for r in results]
+            proc = subprocess.run(cmd, capture_output=True, text=True)
+            log += " ".join(cmd) + "\n" + proc.stdout + proc.stderr
+            if proc.returncode != 0:
+                failed = [(None, proc.stdout + proc.stderr, proc.returncode)]
+        if lib_path == LIB_PATH:
+            with open(os.path.join(HERE, "build.log"), "w") as f:
+                f.write(log)
+        if failed:
+            raise RuntimeError("nvcc failed:\n" + "\n".join(r[1][-4000:] for r in failed))
+        os.replace(lib_path + ".tmp", lib_path)
+    finally:
+        shutil.rmtree(objdir, ignore_errors=True)
     if verbose:
         print(log)
-    return LIB_PATH
+    return lib_path

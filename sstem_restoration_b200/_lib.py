@@ -32,7 +32,8 @@ WARP_NEAREST = 1
 
 #: every symbol include/sstem_b200.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = (
-    "sstem_sepconv_forward", "sstem_sepconv_backward", "sstem_warp_forward", "sstem_image_warp",
+    "sstem_sepconv_forward", "sstem_sepconv_backward", "sstem_interp_tail_forward", "sstem_interp_tail_backward",
+    "sstem_warp_forward", "sstem_image_warp",
     "sstem_fp32_peak_probe", "sstem_launch_count", "sstem_abi_version", "sstem_error_string",
 )
 
@@ -61,6 +62,10 @@ def load() -> ctypes.CDLL:
         lib.sstem_sepconv_forward.restype = ctypes.c_int
         lib.sstem_sepconv_backward.argtypes = [_c_p] * 7 + [_c_i64] * 4 + [_c_i32, _c_u32, _c_p]
         lib.sstem_sepconv_backward.restype = ctypes.c_int
+        lib.sstem_interp_tail_forward.argtypes = [_c_p, _c_p, _c_i64] + [_c_p] * 5 + [_c_i64] * 4 + [_c_i32, _c_u32, _c_p]
+        lib.sstem_interp_tail_forward.restype = ctypes.c_int
+        lib.sstem_interp_tail_backward.argtypes = [_c_p, _c_p, _c_p, _c_i64] + [_c_p] * 8 + [_c_i64] * 4 + [_c_i32, _c_u32, _c_p]
+        lib.sstem_interp_tail_backward.restype = ctypes.c_int
         lib.sstem_warp_forward.argtypes = [_c_p, _c_p, ctypes.POINTER(_c_i64), _c_p, _c_i64, _c_i64, _c_i64, _c_i64, _c_i32, _c_p]
         lib.sstem_warp_forward.restype = ctypes.c_int
         lib.sstem_image_warp.argtypes = [_c_p, _c_i32, _c_p, _c_p, _c_p, _c_i64, _c_i64, _c_i64, _c_i64, _c_i32, _c_p]

@@ -64,6 +64,55 @@ extern "C" int sstem_sepconv_backward(const float* grad_output, const float* inp
     return e;
 }
 
+static int check_tail_args(int64_t B, int64_t C, int64_t H, int64_t W, int32_t K, uint32_t flags, int64_t bstride) {
+    if (int e = check_sepconv_dims(B, C, H, W, K)) return e;
+    if (K != 51) return SSTEM_E_SHAPE;                  // the reference's only tap count; no generic tail
+    if (flags & ~SSTEM_SEPCONV_GRAY_REPLICATED) return SSTEM_E_FLAG;
+    if (bstride < C * H * W) return SSTEM_E_SHAPE;
+    return 0;
+}
+
+extern "C" int sstem_interp_tail_forward(const float* frame1, const float* frame2, int64_t frame_batch_stride,
+                                         const float* k1v, const float* k1h, const float* k2v, const float* k2h,
+                                         float* output, int64_t B, int64_t C, int64_t H, int64_t W,
+                                         int32_t K, uint32_t flags, void* stream) {
+    if (!frame1 || !frame2 || !k1v || !k1h || !k2v || !k2h || !output) return SSTEM_E_NULL;
+    if (int e = check_tail_args(B, C, H, W, K, flags, frame_batch_stride)) return e;
+    if (!aligned4(frame1) || !aligned4(frame2) || !aligned4(k1v) || !aligned4(k1h) || !aligned4(k2v) || !aligned4(k2h) ||
+        !aligned4(output))
+        return SSTEM_E_ALIGN;
+    DeviceGuard guard(output);
+    if (guard.err) return guard.err;
+    return launch_interp_tail_fwd_k51(frame1, frame2, frame_batch_stride, k1v, k1h, k2v, k2h, output, B, C, H, W,
+                                      (flags & SSTEM_SEPCONV_GRAY_REPLICATED) != 0, (cudaStream_t)stream);
+}
+
+extern "C" int sstem_interp_tail_backward(const float* grad_output, const float* frame1, const float* frame2,
+                                          int64_t frame_batch_stride,
+                                          const float* k1v, const float* k1h, const float* k2v, const float* k2h,
+                                          float* g_k1v, float* g_k1h, float* g_k2v, float* g_k2h,
+                                          int64_t B, int64_t C, int64_t H, int64_t W,
+                                          int32_t K, uint32_t flags, void* stream) {
+    if (!grad_output || !frame1 || !frame2 || !k1v || !k1h || !k2v || !k2h) return SSTEM_E_NULL;
+    if (!g_k1v && !g_k1h && !g_k2v && !g_k2h) return SSTEM_E_NULL;
+    if (int e = check_tail_args(B, C, H, W, K, flags, frame_batch_stride)) return e;
+    if (!aligned4(grad_output) || !aligned4(frame1) || !aligned4(frame2) || !aligned4(k1v) || !aligned4(k1h) ||
+        !aligned4(k2v) || !aligned4(k2h) || !aligned4(g_k1v) || !aligned4(g_k1h) || !aligned4(g_k2v) || !aligned4(g_k2h))
+        return SSTEM_E_ALIGN;
+    const void* any_out = g_k1v ? g_k1v : (g_k1h ? g_k1h : (g_k2v ? g_k2v : g_k2h));
+    DeviceGuard guard(any_out);
+    if (guard.err) return guard.err;
+    const bool gray = (flags & SSTEM_SEPCONV_GRAY_REPLICATED) != 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (g_k2v || g_k2h)
+        if (int e = launch_interp_tail_bwd_k51(grad_output, frame2, frame_batch_stride, k2v, k2h, g_k2v, g_k2h, B, C, H, W, gray, s))
+            return e;
+    if (g_k1v || g_k1h)
+        if (int e = launch_interp_tail_bwd_k51(grad_output, frame1, frame_batch_stride, k1v, k1h, g_k1v, g_k1h, B, C, H, W, gray, s))
+            return e;
+    return 0;
+}
+
 extern "C" int64_t sstem_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 extern "C" int sstem_abi_version(void) { return SSTEM_ABI_VERSION; }
 

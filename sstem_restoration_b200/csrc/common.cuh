@@ -58,6 +58,11 @@ int launch_sepconv_bwd_taps_generic(const float* g, const float* in, const float
 int launch_sepconv_bwd_taps_k51(const float* g, const float* in, const float* v, const float* h,
                                 float* gv, float* gh,
                                 int64_t B, int64_t C, int64_t H, int64_t W, bool gray, cudaStream_t s);
+int launch_interp_tail_fwd_k51(const float* frame1, const float* frame2, int64_t frame_bstride,
+                               const float* k1v, const float* k1h, const float* k2v, const float* k2h, float* out,
+                               int64_t B, int64_t C, int64_t H, int64_t W, bool gray, cudaStream_t s);
+int launch_interp_tail_bwd_k51(const float* g, const float* frame, int64_t frame_bstride, const float* v, const float* h,
+                               float* gv, float* gh, int64_t B, int64_t C, int64_t H, int64_t W, bool gray, cudaStream_t s);
 int launch_sepconv_bwd_input_k51(const float* g, const float* v, const float* h, float* gi,
                                  int64_t B, int64_t C, int64_t H, int64_t W, cudaStream_t s);
 int launch_sepconv_bwd_input_generic(const float* g, const float* v, const float* h, float* gi,

@@ -1,5 +1,7 @@
-// Tuned 51-tap adaptive separable convolution for sm_100a: forward and the fused
-// gradient w.r.t. the vertical / horizontal taps.
+// Tuned 51-tap adaptive separable convolution for sm_100a: device code shared by the
+// translation units sepconv_k51_{fwd,bwd,gi,tail}.cu (split so that nvcc compiles the ~130
+// kernel instantiations in parallel): forward, the fused gradient w.r.t. the vertical /
+// horizontal taps, the gradient w.r.t. the input and the fused interpolation tail.
 //
 //   out[b,c,y,x] = sum_fy v[b,fy,y,x] * ( sum_fx in[b,c,y+fy,x+fx] * h[b,fx,y,x] )
 //
@@ -29,6 +31,7 @@
 //     they stream through a warp-private cp.async ring, VDEPTH steps ahead.
 //   * The G tap groups of a pixel are summed with a transpose-reduce over
 //     shuffles: once per tile (forward) or once per step for gv (backward).
+#pragma once
 #include "common.cuh"
 
 namespace sstem {
@@ -122,6 +125,71 @@ __device__ __forceinline__ void stage_window(float* tile, const float* __restric
         }
     }
     cp_async_commit();                                  // group 0: the window
+}
+
+// Fused-tail staging (no padded copy of the frame exists): window element (r, col) is pixel
+// (clamp(y0 + r - 25), clamp(x0 + col - 25)) of the UNPADDED frame -- ReplicationPad2d(25) folded into
+// the load (model_interp.py:46,90-91) -- summed over `cs` channel planes (the channel mean of the
+// tail commutes with the convolution, which is linear in the image).  cs <= 3: every plane is
+// fetched with asynchronous 4-byte copies into its own shared-memory plane (`nplanes` = cs of
+// them) and tail_window_reduce() folds them into plane 0 once they have landed, each thread
+// summing exactly the words it copied; cs > 3: plain loads, channel sum, st.shared.
+template <int ROWS, int PITCH>
+__device__ __forceinline__ void stage_window_tail(float* tile, const float* __restrict__ fr, int cs, int nplanes,
+                                                  int x0, int y0, int H, int W, int tid) {
+    constexpr int HALO = K51 / 2;
+    constexpr int CPR = PITCH / 2;                      // a thread owns two adjacent columns
+    constexpr int RSTEP = 128 / CPR;
+    static_assert(PITCH % 2 == 0 && RSTEP >= 1, "window too wide for 128 threads");
+    const int cidx = tid % CPR, r0 = tid / CPR;
+    if (r0 < RSTEP) {
+        const int ca = min(max(x0 + 2 * cidx - HALO, 0), W - 1), cb = min(max(x0 + 2 * cidx + 1 - HALO, 0), W - 1);
+        float* dst = tile + r0 * PITCH + 2 * cidx;
+        const int64_t plane = (int64_t)H * W;
+        if (nplanes == cs) {
+#pragma unroll 2
+            for (int r = r0; r < ROWS; r += RSTEP) {
+                const float* row = fr + (int64_t)min(max(y0 + r - HALO, 0), H - 1) * W;
+                for (int c = 0; c < nplanes; ++c) {
+                    cp_async4(dst + c * (ROWS * PITCH), row + c * plane + ca, true);
+                    cp_async4(dst + c * (ROWS * PITCH) + 1, row + c * plane + cb, true);
+                }
+                dst += RSTEP * PITCH;
+            }
+        } else {
+#pragma unroll 2
+            for (int r = r0; r < ROWS; r += RSTEP) {
+                const float* row = fr + (int64_t)min(max(y0 + r - HALO, 0), H - 1) * W;
+                float sa = __ldg(row + ca), sb = __ldg(row + cb);
+                for (int c = 1; c < cs; ++c) { sa += __ldg(row + c * plane + ca); sb += __ldg(row + c * plane + cb); }
+                dst[0] = sa;
+                dst[1] = sb;
+                dst += RSTEP * PITCH;
+            }
+        }
+    }
+    cp_async_commit();                                  // group 0: the window (possibly empty)
+}
+
+// after the window's cp.async group has completed for THIS thread, before the block barrier
+template <int ROWS, int PITCH>
+__device__ __forceinline__ void tail_window_reduce(float* tile, int nplanes, int tid) {
+    constexpr int CPR = PITCH / 2, RSTEP = 128 / CPR;
+    if (nplanes < 2) return;
+    const int cidx = tid % CPR, r0 = tid / CPR;
+    if (r0 >= RSTEP) return;
+    float2* dst = reinterpret_cast<float2*>(tile + r0 * PITCH + 2 * cidx);
+#pragma unroll 4
+    for (int r = r0; r < ROWS; r += RSTEP) {
+        float2 a = dst[0];
+        for (int c = 1; c < nplanes; ++c) {
+            const float2 q = dst[c * (ROWS * PITCH / 2)];
+            a.x += q.x;
+            a.y += q.y;
+        }
+        dst[0] = a;
+        dst += RSTEP * PITCH / 2;
+    }
 }
 
 // Warp-private ring of vertical taps.  Step st holds, for every row p of the tile,
@@ -478,12 +546,20 @@ __device__ __forceinline__ void bwd_step(const float* __restrict__ prow0, bool n
     }
 }
 
-template <int CC, int G, int R, bool VEC, bool PAIR, bool WV, bool WH, bool ACCUM>
-__global__ void __launch_bounds__(128, 2)
+// TAIL (fused interpolation tail, CC == 1): `in` is the UNPADDED frame [B, cs.., H, W] with batch
+// stride `in_bstride`; the window is its replicate-padded channel sum, gout is [B,1,H,W] and is
+// scaled by `gscale` (= 1/C of the channel mean) -- see interp_tail_fwd_k51_kernel.
+#ifndef SSTEM_BWD_MINB
+#define SSTEM_BWD_MINB 2
+#endif
+template <int CC, int G, int R, bool VEC, bool PAIR, bool WV, bool WH, bool ACCUM, bool TAIL = false>
+__global__ void __launch_bounds__(128, SSTEM_BWD_MINB)
 sepconv_bwd_taps_k51_kernel(const float* __restrict__ gout, const float* __restrict__ in,
                             const float* __restrict__ v, const float* __restrict__ h,
                             float* __restrict__ gv, float* __restrict__ gh,
-                            int C, int c0, int H, int W, int replicas) {
+                            int C, int c0, int H, int W, int replicas,
+                            int64_t in_bstride, int cs, int nplanes, float gscale) {
+    static_assert(!TAIL || CC == 1, "the fused tail works on one (channel-summed) plane");
     constexpr bool accumulate = ACCUM;                   // later channel chunks (C > 3) add into gv / gh
     using Gm = Geo<G, R>;
     constexpr int NP = Gm::NP, NT = Gm::NT;
@@ -495,7 +571,8 @@ sepconv_bwd_taps_k51_kernel(const float* __restrict__ gout, const float* __restr
     const int64_t plane = (int64_t)H * W;
     const int tid = threadIdx.x;
 
-    stage_window<CC, Gm::ROWS, Gm::PITCH, PAIR>(tile, in, (b * C + c0) * (int64_t)IH * IW, x0, y0, IH, IW, tid);
+    if (TAIL) stage_window_tail<Gm::ROWS, Gm::PITCH>(tile, in + b * in_bstride, cs, nplanes, x0, y0, H, W, tid);
+    else stage_window<CC, Gm::ROWS, Gm::PITCH, PAIR>(tile, in, (b * C + c0) * (int64_t)IH * IW, x0, y0, IH, IW, tid);
 
     const int warp = tid >> 5, lane = tid & 31;
     const int pg = lane / G, g = lane % G;
@@ -505,7 +582,7 @@ sepconv_bwd_taps_k51_kernel(const float* __restrict__ gout, const float* __restr
     const bool col_ok = (x0 + xl < W);
 
     VRing<G, R, VEC> vr;
-    vr.init(tile + CC * Gm::ROWS * Gm::PITCH + warp * (VDEPTH * Gm::SLOT), v, b * K51 * plane, plane,
+    vr.init(tile + (TAIL ? nplanes : CC) * Gm::ROWS * Gm::PITCH + warp * (VDEPTH * Gm::SLOT), v, b * K51 * plane, plane,
             y0, x0 + warp * Gm::COLS, H, W, lane);
 #pragma unroll
     for (int st = 0; st < VDEPTH - 1; ++st) {
@@ -535,9 +612,11 @@ sepconv_bwd_taps_k51_kernel(const float* __restrict__ gout, const float* __restr
                 g2[c][pp].x += (col_ok && ya < H) ? __ldg(gp + rc * plane + (int64_t)ya * W) : 0.f;
                 g2[c][pp].y += (col_ok && yb < H) ? __ldg(gp + rc * plane + (int64_t)yb * W) : 0.f;
             }
+            if (TAIL) { g2[c][pp].x *= gscale; g2[c][pp].y *= gscale; }
         }
 
     cp_async_wait<VDEPTH - 2>();
+    if (TAIL) tail_window_reduce<Gm::ROWS, Gm::PITCH>(tile, nplanes, tid);
     __syncthreads();
 
     float2 vcur[NP], vnext[NP];
@@ -785,6 +864,118 @@ sepconv_bwd_input_k51_kernel(const float* __restrict__ gout, const float* __rest
     }
 }
 
+// =====================================================================================
+// Fused interpolation tail -- IFNet.forward, sff_scripts_interp/model/model_interp.py:90-97
+// (sp_scripts_train/networks.py:116-123 runs the same expression twice):
+//   y   = sepconv(ReplicationPad2d(25)(i2), k2v, k2h) + sepconv(ReplicationPad2d(25)(i1), k1v, k1h)
+//   out = mean_c y                                                           -> [B,1,H,W]
+// One launch instead of 2 pads + 2 sepconvs + add + mean: the padding is folded into the window
+// load (clamped coordinates), the channel mean is taken on the IMAGE side (the convolution is
+// linear in the image: mean_c sepconv(i_c) = sepconv(mean_c i_c)), so each frame costs one plane
+// of FMAs instead of C, and both frames accumulate into the same registers.  With
+// SSTEM_SEPCONV_GRAY_REPLICATED the planes are identical copies (what every reference caller
+// feeds: data_provider.py:136-137) and plane 0 is used as is.
+// Same lane mapping / step loop as sepconv_fwd_k51_kernel<1, ...>, run once per frame.
+// =====================================================================================
+struct TailFrames {                                     // indexed by the frame loop straight from the constant bank,
+    const float* frame[2];                              // so the six pointers hold no registers across it
+    const float* v[2];
+    const float* h[2];
+};
+
+template <int G, int R, bool VEC>
+__global__ void __launch_bounds__(128, 2)
+interp_tail_fwd_k51_kernel(const __grid_constant__ TailFrames fa, int64_t frame_bstride, int cs, int nplanes,
+                           float* __restrict__ out, float scale, int H, int W) {
+    using Gm = Geo<G, R>;
+    extern __shared__ __align__(16) float tile[];      // [nplanes][ROWS][PITCH] + 4 warps x v ring
+    const int x0 = blockIdx.x * Gm::TILE_W, y0 = blockIdx.y * R;
+    const int64_t b = blockIdx.z;
+    const int64_t plane = (int64_t)H * W;
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int pg = lane / G, g = lane % G;
+    const int xl = warp * Gm::COLS + pg;
+    const int x = min(x0 + xl, W - 1);
+    const bool novalid = g >= Gm::LAST_VALID_G;
+
+    float2 acc[1][Gm::NP];
+#pragma unroll
+    for (int pp = 0; pp < Gm::NP; ++pp) acc[0][pp] = make_float2(0.f, 0.f);
+
+#pragma unroll 1
+    for (int f = 0; f < 2; ++f) {                       // frame 2 first, as the reference's expression
+        const float* __restrict__ fr = fa.frame[f] + b * frame_bstride;
+        const float* __restrict__ v = fa.v[f];
+        const float* __restrict__ h = fa.h[f];
+        stage_window_tail<Gm::ROWS, Gm::PITCH>(tile, fr, cs, nplanes, x0, y0, H, W, tid);
+
+        VRing<G, R, VEC> vr;
+        vr.init(tile + nplanes * Gm::ROWS * Gm::PITCH + warp * (VDEPTH * Gm::SLOT), v, b * K51 * plane, plane,
+                y0, x0 + warp * Gm::COLS, H, W, lane);
+#pragma unroll
+        for (int st = 0; st < VDEPTH - 1; ++st) vr.issue();
+
+        float2 h2[Gm::NP][Gm::NT];
+        load_h<G, R>(h2, h, b * K51 * plane, plane, y0, x, H, W, g);
+
+        cp_async_wait<VDEPTH - 2>();
+        tail_window_reduce<Gm::ROWS, Gm::PITCH>(tile, nplanes, tid);
+        __syncthreads();
+
+        float2 vcur[Gm::NP], vnext[Gm::NP];
+        vr.read(vcur);
+        const float* prow = tile + xl + g;
+        auto advance = [&]() {
+            cp_async_wait<VDEPTH - 3>();
+            __syncwarp();
+            vr.issue();
+            vr.read(vnext);
+        };
+        float pre[SSTEM_FWD_NPRE + 1];                  // unused at one channel
+#define SSTEM_TAIL_EDGE_STEP(S)                                                    \
+    if ((S) < R - 1 || ((S) >= K51 && (S) < Gm::ROWS)) {                           \
+        advance();                                                                 \
+        fwd_step<1, G, R, S>(prow, novalid, h2, vcur, acc, pre);                   \
+        _Pragma("unroll") for (int pp = 0; pp < Gm::NP; ++pp) vcur[pp] = vnext[pp]; \
+        prow += Gm::PITCH;                                                         \
+    }
+        SSTEM_TAIL_EDGE_STEP(0) SSTEM_TAIL_EDGE_STEP(1) SSTEM_TAIL_EDGE_STEP(2) SSTEM_TAIL_EDGE_STEP(3)
+        SSTEM_TAIL_EDGE_STEP(4) SSTEM_TAIL_EDGE_STEP(5) SSTEM_TAIL_EDGE_STEP(6)
+#pragma unroll 1
+        for (int s = R - 1; s < K51; ++s) {
+            advance();
+            fwd_step<1, G, R, -1>(prow, novalid, h2, vcur, acc, pre);
+#pragma unroll
+            for (int pp = 0; pp < Gm::NP; ++pp) vcur[pp] = vnext[pp];
+            prow += Gm::PITCH;
+        }
+        SSTEM_TAIL_EDGE_STEP(51) SSTEM_TAIL_EDGE_STEP(52) SSTEM_TAIL_EDGE_STEP(53) SSTEM_TAIL_EDGE_STEP(54)
+        SSTEM_TAIL_EDGE_STEP(55) SSTEM_TAIL_EDGE_STEP(56) SSTEM_TAIL_EDGE_STEP(57)
+#undef SSTEM_TAIL_EDGE_STEP
+        static_assert(R <= 8, "edge-step list covers R <= 8");
+        cp_async_wait<0>();                             // the ring's look-ahead copies have landed ...
+        __syncthreads();                                // ... and nobody reads this frame's window any more
+    }
+
+    constexpr int NV = (R >= G) ? R : G;
+    constexpr int PER = NV / G;
+    float val[NV];
+#pragma unroll
+    for (int pp = 0; pp < Gm::NP; ++pp) { val[2 * pp] = acc[0][pp].x; val[2 * pp + 1] = acc[0][pp].y; }
+#pragma unroll
+    for (int i = R; i < NV; ++i) val[i] = 0.f;
+    group_reduce<G, NV>(val, g);
+    if (x0 + xl < W) {
+        float* ob = out + (b * H + y0) * (int64_t)W + x0 + xl;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            const int p = g * PER + j;
+            if (p < R && y0 + p < H) ob[(int64_t)p * W] = val[j] * scale;
+        }
+    }
+}
+
 // ---- host side ------------------------------------------------------------------------------
 template <typename Kern>
 int set_smem_once(Kern kern, size_t smem, bool* done) {
@@ -804,141 +995,5 @@ constexpr size_t smem_bytes() {
     return ((size_t)CC * Geo<G, R>::ROWS * Geo<G, R>::PITCH + 4 * VDEPTH * Geo<G, R>::SLOT) * sizeof(float);
 }
 
-template <int CC, bool VEC, bool PAIR>
-int launch_fwd_variant(const float* in, const float* v, const float* h, float* out,
-                       int64_t B, int C, int c0, int H, int W, int replicas, cudaStream_t s) {
-    constexpr int G = SSTEM_FWD_G, R = SSTEM_FWD_R;
-    constexpr size_t smem = smem_bytes<G, R, CC>();
-    static bool done[16] = {};
-    auto kern = sepconv_fwd_k51_kernel<CC, G, R, VEC, PAIR>;
-    if (int e = set_smem_once(kern, smem, done)) return e;
-    dim3 grid((unsigned)((W + Geo<G, R>::TILE_W - 1) / Geo<G, R>::TILE_W), (unsigned)((H + R - 1) / R), (unsigned)B);
-    kern<<<grid, 128, smem, s>>>(in, v, h, out, C, c0, H, W, replicas);
-    count_launch();
-    return finish_launch();
-}
-
-template <int CC>
-int launch_fwd_chunk(const float* in, const float* v, const float* h, float* out,
-                     int64_t B, int C, int c0, int H, int W, int replicas, cudaStream_t s) {
-    const bool vec = ((W & 3) == 0) && aligned16(v);
-    const bool pair = (((W + K51 - 1) & 1) == 0) && ((reinterpret_cast<uintptr_t>(in) & 7u) == 0);
-    if (vec && pair) return launch_fwd_variant<CC, true, true>(in, v, h, out, B, C, c0, H, W, replicas, s);
-    if (vec) return launch_fwd_variant<CC, true, false>(in, v, h, out, B, C, c0, H, W, replicas, s);
-    if (pair) return launch_fwd_variant<CC, false, true>(in, v, h, out, B, C, c0, H, W, replicas, s);
-    return launch_fwd_variant<CC, false, false>(in, v, h, out, B, C, c0, H, W, replicas, s);
-}
-
-template <int CC, bool VEC, bool PAIR, bool WV, bool WH>
-int launch_bwd_variant(const float* g, const float* in, const float* v, const float* h, float* gv, float* gh,
-                       int64_t B, int C, int c0, int H, int W, int accumulate, int replicas, cudaStream_t s) {
-    constexpr int G = SSTEM_BWD_G, R = SSTEM_BWD_R;
-    constexpr size_t smem = smem_bytes<G, R, CC>();
-    static bool done[16] = {};
-    dim3 grid((unsigned)((W + Geo<G, R>::TILE_W - 1) / Geo<G, R>::TILE_W), (unsigned)((H + R - 1) / R), (unsigned)B);
-    if (accumulate) {
-        static bool done_a[16] = {};
-        auto kern = sepconv_bwd_taps_k51_kernel<CC, G, R, VEC, PAIR, WV, WH, true>;
-        if (int e = set_smem_once(kern, smem, done_a)) return e;
-        kern<<<grid, 128, smem, s>>>(g, in, v, h, gv, gh, C, c0, H, W, replicas);
-    } else {
-        auto kern = sepconv_bwd_taps_k51_kernel<CC, G, R, VEC, PAIR, WV, WH, false>;
-        if (int e = set_smem_once(kern, smem, done)) return e;
-        kern<<<grid, 128, smem, s>>>(g, in, v, h, gv, gh, C, c0, H, W, replicas);
-    }
-    count_launch();
-    return finish_launch();
-}
-
-template <int CC, bool WV, bool WH>
-int launch_bwd_chunk(const float* g, const float* in, const float* v, const float* h, float* gv, float* gh,
-                     int64_t B, int C, int c0, int H, int W, int accumulate, int replicas, cudaStream_t s) {
-    const bool vec = ((W & 3) == 0) && aligned16(v);
-    const bool pair = (((W + K51 - 1) & 1) == 0) && ((reinterpret_cast<uintptr_t>(in) & 7u) == 0);
-    if (vec && pair) return launch_bwd_variant<CC, true, true, WV, WH>(g, in, v, h, gv, gh, B, C, c0, H, W, accumulate, replicas, s);
-    if (vec) return launch_bwd_variant<CC, true, false, WV, WH>(g, in, v, h, gv, gh, B, C, c0, H, W, accumulate, replicas, s);
-    if (pair) return launch_bwd_variant<CC, false, true, WV, WH>(g, in, v, h, gv, gh, B, C, c0, H, W, accumulate, replicas, s);
-    return launch_bwd_variant<CC, false, false, WV, WH>(g, in, v, h, gv, gh, B, C, c0, H, W, accumulate, replicas, s);
-}
-
-template <bool WV, bool WH>
-int launch_bwd_all(const float* g, const float* in, const float* v, const float* h, float* gv, float* gh,
-                   int64_t B, int C, int H, int W, bool gray, cudaStream_t s) {
-    if (gray && C > 1)                                     // identical planes: one channel, summed upstream gradient
-        return launch_bwd_chunk<1, WV, WH>(g, in, v, h, gv, gh, B, C, 0, H, W, 0, C, s);
-    int c0 = 0;
-    while (c0 < C) {                                       // channel chunks of <= 3; later chunks accumulate
-        const int cc = (C - c0) < 3 ? (C - c0) : 3;
-        const int acc = c0 > 0;
-        int e;
-        if (cc == 3) e = launch_bwd_chunk<3, WV, WH>(g, in, v, h, gv, gh, B, C, c0, H, W, acc, 1, s);
-        else if (cc == 2) e = launch_bwd_chunk<2, WV, WH>(g, in, v, h, gv, gh, B, C, c0, H, W, acc, 1, s);
-        else e = launch_bwd_chunk<1, WV, WH>(g, in, v, h, gv, gh, B, C, c0, H, W, acc, 1, s);
-        if (e) return e;
-        c0 += cc;
-    }
-    return 0;
-}
-
 }  // namespace
-
-int launch_sepconv_fwd_k51(const float* in, const float* v, const float* h, float* out,
-                           int64_t B, int64_t C, int64_t H, int64_t W, bool gray, cudaStream_t s) {
-    if (B > 65535 || (H + SSTEM_FWD_R - 1) / SSTEM_FWD_R > 65535)   // grid.y / grid.z limits
-        return launch_sepconv_fwd_generic(in, v, h, out, B, C, H, W, 51, false, s);
-    if (gray && C > 1)                                     // identical planes: compute one, write C copies
-        return launch_fwd_chunk<1>(in, v, h, out, B, (int)C, 0, (int)H, (int)W, (int)C, s);
-    int c0 = 0;
-    while (c0 < C) {                                       // channels in chunks of <= 3 (taps re-read per chunk)
-        const int cc = (C - c0) < 3 ? (int)(C - c0) : 3;
-        int e;
-        if (cc == 3) e = launch_fwd_chunk<3>(in, v, h, out, B, (int)C, c0, (int)H, (int)W, 1, s);
-        else if (cc == 2) e = launch_fwd_chunk<2>(in, v, h, out, B, (int)C, c0, (int)H, (int)W, 1, s);
-        else e = launch_fwd_chunk<1>(in, v, h, out, B, (int)C, c0, (int)H, (int)W, 1, s);
-        if (e) return e;
-        c0 += cc;
-    }
-    return 0;
-}
-
-int launch_sepconv_bwd_taps_k51(const float* g, const float* in, const float* v, const float* h,
-                                float* gv, float* gh, int64_t B, int64_t C, int64_t H, int64_t W, bool gray, cudaStream_t s) {
-    if (B > 65535 || (H + SSTEM_BWD_R - 1) / SSTEM_BWD_R > 65535)
-        return launch_sepconv_bwd_taps_generic(g, in, v, h, gv, gh, B, C, H, W, 51, s);
-    if (gv && gh) return launch_bwd_all<true, true>(g, in, v, h, gv, gh, B, (int)C, (int)H, (int)W, gray, s);
-    if (gv) return launch_bwd_all<true, false>(g, in, v, h, gv, gh, B, (int)C, (int)H, (int)W, gray, s);
-    return launch_bwd_all<false, true>(g, in, v, h, gv, gh, B, (int)C, (int)H, (int)W, gray, s);
-}
-
-int launch_sepconv_bwd_input_k51(const float* g, const float* v, const float* h, float* gi,
-                                 int64_t B, int64_t C, int64_t H, int64_t W, cudaStream_t s) {
-    constexpr int G = 4, R = 8;
-    if (B > 65535 || (H + R - 1) / R > 65535)
-        return launch_sepconv_bwd_input_generic(g, v, h, gi, B, C, H, W, 51, s);
-    cudaError_t e = cudaMemsetAsync(gi, 0, (size_t)B * C * (H + K51 - 1) * (W + K51 - 1) * sizeof(float), s);
-    if (e != cudaSuccess) return (int)e;
-    const bool vec = ((W & 3) == 0) && aligned16(v);
-    dim3 grid((unsigned)((W + Geo<G, R>::TILE_W - 1) / Geo<G, R>::TILE_W), (unsigned)((H + R - 1) / R), (unsigned)B);
-    int c0 = 0;
-    while (c0 < C) {
-        const int cc = (C - c0) < 3 ? (int)(C - c0) : 3;
-#define SSTEM_GI_LAUNCH(CC_, VEC_)                                                                   \
-    {                                                                                                 \
-        constexpr size_t smem = smem_bytes<G, R, CC_>();                                              \
-        static bool done[16] = {};                                                                    \
-        auto kern = sepconv_bwd_input_k51_kernel<CC_, R, VEC_>;                                    \
-        if (int err = set_smem_once(kern, smem, done)) return err;                                    \
-        kern<<<grid, 128, smem, s>>>(g, v, h, gi, (int)C, c0, (int)H, (int)W);                        \
-    }
-        if (cc == 3) { if (vec) SSTEM_GI_LAUNCH(3, true) else SSTEM_GI_LAUNCH(3, false) }
-        else if (cc == 2) { if (vec) SSTEM_GI_LAUNCH(2, true) else SSTEM_GI_LAUNCH(2, false) }
-        else { if (vec) SSTEM_GI_LAUNCH(1, true) else SSTEM_GI_LAUNCH(1, false) }
-#undef SSTEM_GI_LAUNCH
-        count_launch();
-        if (int err = finish_launch()) return err;
-        c0 += cc;
-    }
-    return 0;
-}
-
 }  // namespace sstem

@@ -172,3 +172,92 @@ class ModuleSepconv(torch.nn.Module):
 
     def forward(self, tenInput, tenVertical, tenHorizontal):
         return _FunctionSepconv.apply(tenInput, tenVertical, tenHorizontal)
+
+
+# ---------------------------------------------------------------------------------------------
+# Fused interpolation tail
+# ---------------------------------------------------------------------------------------------
+def _frame_view(t):
+    """A frame as the C ABI wants it: planes contiguous, any batch stride (x[:, :3] of a
+    [B,6,H,W] tensor qualifies as is -- model_interp.py:56-57)."""
+    B, C, H, W = t.shape
+    ok = t.stride(3) == 1 and t.stride(2) == W and (C == 1 or t.stride(1) == H * W) and (B == 1 or t.stride(0) >= C * H * W)
+    if not ok:
+        t = t.contiguous()
+    return t, (t.stride(0) if B > 1 else C * H * W)
+
+
+class _InterpolationTail(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, i1, i2, k1v, k1h, k2v, k2h):
+        for t in (i1, i2, k1v, k1h, k2v, k2h):
+            if t.is_cuda == False:
+                raise NotImplementedError()  # as SeparableConvolution.py:47-48: no CPU version
+            if t.dtype != torch.float32:
+                raise TypeError("interpolation_tail: float32 tensors required")
+        assert i1.shape == i2.shape and i1.dim() == 4
+        B, C, H, W = i1.shape
+        for k in (k1v, k1h, k2v, k2h):
+            assert tuple(k.shape) == (B, 51, H, W)          # SeparableConvolution.py:31 -- 51 taps
+            assert (k.is_contiguous() == True)
+        i1, bs1 = _frame_view(i1)
+        i2, bs2 = _frame_view(i2)
+        if bs1 != bs2:
+            i1, i2 = i1.contiguous(), i2.contiguous()
+            bs1 = bs2 = C * H * W
+        gray = C > 1 and _GRAY != "off" and (
+            _GRAY == "assert" or all(bool(torch.equal(f[:, 0], f[:, c])) for f in (i1, i2) for c in range(1, C)))
+        out = torch.empty((B, 1, H, W), dtype=torch.float32, device=i1.device)
+        ctx.save_for_backward(i1, i2, k1v, k1h, k2v, k2h)
+        ctx.tail = (bs1, gray)
+        if out.numel() == 0:
+            return out
+        code = _lib.load().sstem_interp_tail_forward(
+            i1.data_ptr(), i2.data_ptr(), bs1, k1v.data_ptr(), k1h.data_ptr(), k2v.data_ptr(), k2h.data_ptr(),
+            out.data_ptr(), B, C, H, W, 51, _lib.SEPCONV_GRAY_REPLICATED if gray else 0, _stream_ptr(i1))
+        if code:
+            _lib.check(code, "sstem_interp_tail_forward")
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        i1, i2, k1v, k1h, k2v, k2h = ctx.saved_tensors
+        bs, gray = ctx.tail
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            raise NotImplementedError("interpolation_tail: the frames are data; no gradient w.r.t. them "
+                                      "(use SeparableConvolution on the padded frames for that)")
+        need = ctx.needs_input_grad[2:6]
+        B, C, H, W = i1.shape
+        grad_output = grad_output.contiguous()
+        grads = [torch.empty_like(k) if n else None for k, n in zip((k1v, k1h, k2v, k2h), need)]
+        if any(need) and grad_output.numel() > 0:
+            code = _lib.load().sstem_interp_tail_backward(
+                grad_output.data_ptr(), i1.data_ptr(), i2.data_ptr(), bs,
+                k1v.data_ptr(), k1h.data_ptr(), k2v.data_ptr(), k2h.data_ptr(),
+                *[g.data_ptr() if g is not None else None for g in grads],
+                B, C, H, W, 51, _lib.SEPCONV_GRAY_REPLICATED if gray else 0, _stream_ptr(i1))
+            if code:
+                _lib.check(code, "sstem_interp_tail_backward")
+        return (None, None, *grads)
+
+
+def interpolation_tail(i1, i2, k1v, k1h, k2v, k2h):
+    """One launch for the expression every IFNet ends with (model_interp.py:90-97,
+    sp_scripts_train/networks.py:116-123)::
+
+        y = separable_conv(pad(i2), k2v, k2h) + separable_conv(pad(i1), k1v, k1h)   # pad = ReplicationPad2d(25)
+        output = torch.mean(y, dim=1, keepdim=True)
+
+    ``i1`` / ``i2``: UNPADDED frames [B,C,H,W] (views ``x[:, :3]`` / ``x[:, 3:6]`` are taken as they
+    are); taps [B,51,H,W]; returns [B,1,H,W].  Differentiable w.r.t. the four tap tensors.  The
+    gray x3 shortcut follows :func:`set_gray_replicated`.  Agrees with the unfused expression to
+    fp32 rounding (the channel mean is taken before the convolution, which is linear in the image).
+    """
+    return _InterpolationTail.apply(i1, i2, k1v, k1h, k2v, k2h)
+
+
+class ModuleInterpolationTail(torch.nn.Module):
+    """``nn.Module`` form of :func:`interpolation_tail` (stateless)."""
+
+    def forward(self, i1, i2, k1v, k1h, k2v, k2h):
+        return _InterpolationTail.apply(i1, i2, k1v, k1h, k2v, k2h)

@@ -114,3 +114,36 @@ def test_sepconv_oracle_matches_reference_cuda_outputs(golden_dir):
         assert np.array_equal(oracle.sepconv_grad_vertical_reforder(g, inp, h).view(np.uint32), ref[name + "_gv"].view(np.uint32)), name
         assert np.array_equal(oracle.sepconv_grad_horizontal_reforder(g, inp, v).view(np.uint32), ref[name + "_gh"].view(np.uint32)), name
         assert not ref[name + "_gi"].any(), "the reference leaves grad_input zero"
+
+
+# ------------------------------------------------------------------ interpolation tail oracle
+def test_interp_tail_restatement_matches_torch_expression():
+    """oracle.interp_tail_reference against model_interp.py:90-97 evaluated with torch CPU ops
+    (nn.ReplicationPad2d, torch.mean) around the reference-order sepconv."""
+    r = np.random.default_rng(5)
+    B, C, H, W = 2, 3, 6, 9
+    i1, i2 = r.random((B, C, H, W), dtype=np.float32), r.random((B, C, H, W), dtype=np.float32)
+    from sstem_restoration_b200 import synth
+    k1v, k1h, k2v, k2h = (synth.unit_taps(B, 51, H, W, seed=40 + i) for i in range(4))
+    pad = torch.nn.ReplicationPad2d(25)
+    p1, p2 = pad(torch.from_numpy(i1)).numpy(), pad(torch.from_numpy(i2)).numpy()
+    assert np.array_equal(p1, oracle._replicate_pad(i1))
+    y = torch.from_numpy(oracle.sepconv_forward_reforder(p2, k2v, k2h)) + torch.from_numpy(oracle.sepconv_forward_reforder(p1, k1v, k1h))
+    want = torch.mean(y, dim=1, keepdim=True).numpy()
+    got = oracle.interp_tail_reference(i1, i2, k1v, k1h, k2v, k2h)
+    assert got.shape == want.shape and float(np.abs(got - want).max()) <= 1.2e-7
+    assert float(np.abs(got - oracle.interp_tail_f64(i1, i2, k1v, k1h, k2v, k2h)).max()) <= 1e-5
+
+
+def test_interp_tail_grads_match_autograd_f64():
+    r = np.random.default_rng(6)
+    B, C, H, W = 1, 3, 3, 4
+    i1, i2 = r.random((B, C, H, W), dtype=np.float32), r.random((B, C, H, W), dtype=np.float32)
+    taps = [r.standard_normal((B, 51, H, W)).astype(np.float32) / 51 for _ in range(4)]
+    g = r.standard_normal((B, 1, H, W)).astype(np.float32)
+    pad = torch.nn.ReplicationPad2d(25)
+    t = [torch.from_numpy(a).double().requires_grad_(True) for a in taps]
+    y = _torch_sepconv_f64(pad(torch.from_numpy(i2).double()), t[2], t[3]) + _torch_sepconv_f64(pad(torch.from_numpy(i1).double()), t[0], t[1])
+    torch.mean(y, dim=1, keepdim=True).backward(torch.from_numpy(g).double())
+    for got, tt in zip(oracle.interp_tail_grads_f64(g, i1, i2, *taps), t):
+        assert float(np.abs(got - tt.grad.numpy()).max()) <= 1e-6

@@ -62,6 +62,31 @@ def main():
                               "fwd_gpix_s": round(px / ms_f / 1e6, 3), "bwd_gpix_s": round(px / ms_b / 1e6, 3),
                               "fwd_tapGBs": round(px * 408 / ms_f / 1e6, 1), "bwd_GBs": round(px * 840 / ms_b / 1e6, 1)}))
             del gv, gh
+        if "tail" in what and C == 3:
+            # fused interpolation tail vs the unfused expression it replaces (model_interp.py:90-97)
+            f1, f2 = torch.rand((B, 1, H, W), device=dev).expand(B, 3, H, W).contiguous(), torch.rand((B, 1, H, W), device=dev).expand(B, 3, H, W).contiguous()
+            v2, h2 = torch.softmax(torch.randn((B, K, H, W), device=dev), 1), torch.softmax(torch.randn((B, K, H, W), device=dev), 1)
+            pad = torch.nn.ReplicationPad2d(25)
+
+            def unfused():
+                y = pkg.SeparableConvolution.apply(pad(f2), v2, h2) + pkg.SeparableConvolution.apply(pad(f1), v, h)
+                return torch.mean(y, dim=1, keepdim=True)
+            res = {"op": "interp_tail", "shape": [B, C, H, W], "ms_unfused": round(timeit(unfused), 4)}
+            for mode in ("off", "assert"):
+                pkg.set_gray_replicated(mode)
+                ms = timeit(lambda: pkg.interpolation_tail(f1, f2, v, h, v2, h2))
+                res["ms_fused_gray_" + mode] = round(ms, 4)
+                res["gpix_s_gray_" + mode] = round(px / ms / 1e6, 3)
+                res["tapGBs_gray_" + mode] = round(px * 816 / ms / 1e6, 1)
+            pkg.set_gray_replicated("off")
+            gvs = [torch.empty_like(v) for _ in range(4)]
+            go = torch.randn((B, 1, H, W), device=dev)
+            for flag in (0, 2):
+                ms = timeit(lambda: lib.sstem_interp_tail_backward(go.data_ptr(), f1.data_ptr(), f2.data_ptr(), 3 * H * W, v.data_ptr(), h.data_ptr(), v2.data_ptr(), h2.data_ptr(),
+                                                                   *[t.data_ptr() for t in gvs], B, C, H, W, K, flag, st), reps=3, warm=1)
+                res["ms_bwd_flag%d" % flag] = round(ms, 4)
+            print(json.dumps(res))
+            del f1, f2, v2, h2, gvs, go
         if "gi" in what:
             gi = torch.empty_like(inp)
             ms = timeit(lambda: lib.sstem_sepconv_backward(g.data_ptr(), inp.data_ptr(), v.data_ptr(), h.data_ptr(), gi.data_ptr(), None, None, B, C, H, W, K, 0, st), reps=2, warm=1)
