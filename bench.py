@@ -320,6 +320,7 @@ def run_gpu_arm(args):
 
     # ---- warp (config 4) on the same device, reported beside the headline -------------------
     warp = run_warp(args, pkg, dev) if not args.no_warp else None
+    tail = run_tail(pkg, dev, B, H, W) if (not args.no_warp and rank == 0) else None
 
     if rank != 0:
         if world > 1:
@@ -370,7 +371,7 @@ def run_gpu_arm(args):
         "cpu_baseline": {"value": round(cpu_val, 4), "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": cpu_sample},
         "e2e": e2e, "gpu_launches": int(lsum.item()), "clocks": clocks,
         "extra": {"fwd_mpix_per_s": round(px_call / (fwd_ms * 1e-3) / 1e6, 1), "bwd_taps_mpix_per_s": round(px_call / (bwd_ms * 1e-3) / 1e6, 1),
-                  "warp": warp, "gray_x3_shortcut": gray, "ms_per_step_by_rank": per_rank},
+                  "warp": warp, "gray_x3_shortcut": gray, "fused_interp_tail": tail, "ms_per_step_by_rank": per_rank},
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -441,24 +442,21 @@ def run_e2e(args, pkg, dev, sets, calls, B, C, H, W, world, dist):
                    "grad_horizontal; two samples per chunk on 3 streams (H2D, C-ABI fwd+bwd kernels, D2H overlapped); the step's two calls are queued back to back and joined once"}
 
 
-def run_warp(args, pkg, dev):
-    """Config 4 warp: im[1,3,2048,2048], planar-strided flow view; rotating buffer sets > L2."""
+def _time_warp(pkg, dev, H, W, nsets, reps):
     import numpy as np
     import torch
     from sstem_restoration_b200 import synth
-    H = W = 2048
     st = pkg.SpatialTransformation(True)
-    nsets = 6                                          # 6 x 134 MB = 805 MB >> 126 MB L2
     flow_np, _ = synth.random_fold_flow(H, W, 555)
+    planar0 = torch.from_numpy(np.ascontiguousarray(flow_np.transpose(2, 0, 1))[None]).to(dev)
+    sec = torch.from_numpy(synth.em_section(H, W, 50).astype(np.float32) / 255.0).to(dev)
     bufs = []
     for i in range(nsets):
-        im = torch.from_numpy(np.repeat((synth.em_section(H, W, 50 + i).astype(np.float32) / 255.0)[None, None], 3, 1)).to(dev)
-        planar = torch.from_numpy(np.ascontiguousarray(flow_np.transpose(2, 0, 1))[None]).to(dev) + 0.01 * i
-        bufs.append((im, planar.permute(0, 2, 3, 1)))
+        im = torch.roll(sec, shifts=17 * i, dims=1)[None, None].expand(1, 3, H, W).contiguous()   # gray x3, as the callers feed
+        bufs.append((im, (planar0 + 0.01 * i).permute(0, 2, 3, 1)))
     for im, fl in bufs:
         st(im, fl)
     torch.cuda.synchronize()
-    reps = 5
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
@@ -467,9 +465,60 @@ def run_warp(args, pkg, dev):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / (reps * nsets)
-    gbs = BYTES_WARP(3) * H * W / (ms * 1e-3) / 1e9
-    return {"metric": "warp_gb_per_s", "gbs": gbs, "ms": ms, "gpix_per_s": H * W / (ms * 1e-3) / 1e9,
-            "config": "c4 warp: im[1,3,2048,2048], flow planar [1,2,2048,2048] viewed as [1,2048,2048,2], SFF fold flow; 6 rotating buffer sets (805 MB > L2)"}
+    del bufs
+    torch.cuda.empty_cache()
+    return ms
+
+
+def run_warp(args, pkg, dev):
+    """Flow warp (SpatialTransformation) on the SFF fold flow, planar-strided flow view, rotating buffer sets > L2:
+    the config-5 section size (4096^2, the roofline entry) and the config-4 size (2048^2, launch-latency share larger)."""
+    ms5 = _time_warp(pkg, dev, 4096, 4096, nsets=3, reps=5)       # 3 x 537 MB
+    ms4 = _time_warp(pkg, dev, 2048, 2048, nsets=6, reps=5)       # 6 x 134 MB
+    g = lambda n, ms: BYTES_WARP(3) * n * n / (ms * 1e-3) / 1e9
+    return {"metric": "warp_gb_per_s", "gbs": g(4096, ms5), "ms": ms5, "gpix_per_s": 4096 * 4096 / (ms5 * 1e-3) / 1e9,
+            "config": "c5 section warp: im[1,3,4096,4096], flow planar [1,2,4096,4096] viewed as [1,4096,4096,2], SFF fold flow "
+                      "(gen_flow, seed 555); 3 rotating buffer sets (1.6 GB > L2); through the SpatialTransformation module",
+            "c4_2048": {"gbs": g(2048, ms4), "ms": ms4, "gpix_per_s": 2048 * 2048 / (ms4 * 1e-3) / 1e9,
+                        "config": "c4 warp: im[1,3,2048,2048], same flow family; 6 rotating buffer sets (805 MB > L2)"}}
+
+
+def run_tail(pkg, dev, B, H, W, reps=5):
+    """Fused interpolation tail against the unfused expression it replaces, gray x3 frames."""
+    import torch
+    gen = torch.Generator(device=dev).manual_seed(11)
+    f = [torch.rand((B, 1, H, W), device=dev, generator=gen).expand(B, 3, H, W).contiguous() for _ in range(2)]
+    taps = [torch.softmax(torch.randn((B, K, H, W), device=dev, generator=gen), 1) for _ in range(4)]
+    pad = torch.nn.ReplicationPad2d(K // 2)
+
+    def unfused():
+        y = pkg.SeparableConvolution.apply(pad(f[1]), taps[2], taps[3]) + pkg.SeparableConvolution.apply(pad(f[0]), taps[0], taps[1])
+        return torch.mean(y, dim=1, keepdim=True)
+
+    def timed(fn):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    res = {"shape": [B, 3, H, W], "ms_unfused_expression": round(timed(unfused), 4)}
+    for mode in ("off", "assert"):
+        pkg.set_gray_replicated(mode)
+        try:
+            ms = timed(lambda: pkg.interpolation_tail(f[0], f[1], *taps))
+        finally:
+            pkg.set_gray_replicated("off")
+        res["ms_fused_gray_" + mode] = round(ms, 4)
+        res["mpix_per_s_gray_" + mode] = round(B * H * W / (ms * 1e-3) / 1e6, 1)
+    res["note"] = ("interpolation_tail = 2x ReplicationPad2d + 2x sepconv + add + channel mean in one launch "
+                   "(model_interp.py:90-97); 816 B of taps per output pixel; NOT the headline")
+    return res
 
 
 def main():

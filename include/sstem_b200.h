@@ -184,6 +184,38 @@ int sstem_image_warp(const void* im, int32_t pix_type, const float* flow,
                      int32_t mode, void* stream);
 
 /*
+ * GPU-resident SFF (support-film fold) degradation -- one pass for simu_sff/simuSFF.py:113-121:
+ *   flow, mask = gen_flow(h, w, k, b, line_width, fold_width, dis_k)   (simu_sff/flow_synthesis.py:27-83)
+ *   deformed   = image_warp(img, flow, mode='bilinear')                (simu_sff/image_warp.py:3-111)
+ *   out        = (deformed * mask).astype(np.uint8)
+ * bit-equal to the reference's numpy run (FP64 distance field in numpy's operation order, float32
+ * flow, numpy-semantics bilinear gather, uint8 truncation).
+ *   img      [batch, h, w] uint8 (grayscale sections)
+ *   params   DEVICE [batch][8] float64: k, b, sqrt(k*k+1), line_width, fold_width, dis_k,
+ *            sin(atan(1/k)), cos(atan(1/k)) -- the scalars flow_synthesis.py:31,64-71 derives with
+ *            Python's math module (passed in so the device never re-derives a libm result)
+ *   out      [batch, h, w] uint8
+ *   flow_out [batch, h, w, 2] float32 or NULL;  mask_out [batch, h, w] uint8 (0/1) or NULL
+ *   stats    DEVICE [batch][2] int64, overwritten: number of zero pixels of `out` (the accept test
+ *            of simuSFF.py:125-130) and the sum of its pixels (np.mean for sstem_sff_contrast)
+ */
+int sstem_sff_degrade(const uint8_t* img, const double* params, uint8_t* out, float* flow_out,
+                      uint8_t* mask_out, int64_t* stats, int64_t batch, int64_t h, int64_t w, void* stream);
+
+/*
+ * Regional-contrast step of simuSFF.py:134-144 (`noise`), in place on the image sstem_sff_degrade
+ * produced: inside the box p <- uint8(ran * (p - mean) + mean) with mean = np.mean(img); pixels
+ * that are 0 stay 0.
+ *   img      [batch, h, w] uint8, modified in place
+ *   stats    DEVICE [batch][2] int64 as written by sstem_sff_degrade for the same image
+ *   params   DEVICE [batch][8] float64: ran_reginal_contrast, box row0, box col0, box height, box
+ *            width, 3 unused
+ *   max_box_h / max_box_w: largest box of the batch (grid size)
+ */
+int sstem_sff_contrast(uint8_t* img, const int64_t* stats, const double* params,
+                       int64_t batch, int64_t h, int64_t w, int64_t max_box_h, int64_t max_box_w, void* stream);
+
+/*
  * FP32 FMA-pipe probe: runs a register-resident FFMA loop on every SM of the
  * current device and returns the sustained rate in TFLOP/s (2 flop per FMA).
  * bench.py uses it as the measured denominator of the sepconv roofline

@@ -286,3 +286,61 @@ def image_warp_restated(im, flow, mode="bilinear", return_float=False):
         valf = np.squeeze(valf, axis=0)
     u8 = valf.astype(np.uint8)
     return (u8, valf) if return_float else u8
+
+
+# --------------------------------------------------------------------------- SFF simulation (config 1)
+def _sff_border_point(side, height, width, offset, crop_size, rng):
+    x = rng.randint(1, (width if side in (1, 3) else height) - 1)
+    while x < offset or x > crop_size - 50:
+        x = rng.randint(1, width - 1)
+    return {1: [0, x], 2: [x, width], 3: [height, x], 4: [x, 0]}[side]
+
+
+def sff_get_two_points(height, width, offset, crop_size, rng):
+    """simu_sff/simuSFF.py:42-94, same sequence of random draws."""
+    k1 = rng.randint(1, 4)
+    k2 = rng.randint(1, 4)
+    while k1 == k2:
+        k2 = rng.randint(1, 4)
+    return (_sff_border_point(k1, height, width, offset, crop_size, rng),
+            _sff_border_point(k2, height, width, offset, crop_size, rng))
+
+
+def sff_degradation_restated(img, crop_size, rng, offset=50):
+    """simu_sff/simuSFF.py:96-132 restated on numpy: draw a fold line, gen_flow
+    (flow_synthesis.py:27-83, via the golden-pinned restatement in synth.gen_flow), numpy
+    image_warp (image_warp_restated), mask multiply, uint8 cast; repeat until >= 100 zero pixels.
+    -> (deformed uint8, flow float32 [H,W,2], mask float64)."""
+    import math
+    from sstem_restoration_b200 import synth            # numpy-only restatement, pinned by gen_flow_ref.npz
+    while True:
+        height = width = crop_size
+        line_width = rng.randint(5, 20)
+        fold_width = rng.randint(10, 80)
+        dist = lambda a, c: math.sqrt((a[0] - c[0]) ** 2 + (a[1] - c[1]) ** 2)
+        p1, p2 = sff_get_two_points(height, width, offset, crop_size, rng)
+        while dist(p1, p2) < crop_size / 2:
+            p1, p2 = sff_get_two_points(height, width, offset, crop_size, rng)
+        dis_k = rng.uniform(0.00001, 0.1)
+        k, b = synth.gen_line(p1, p2)
+        flow, mask = synth.gen_flow(height, width, k, b, line_width, fold_width, dis_k)
+        deformed = image_warp_restated(img, flow, mode="bilinear")
+        deformed = (deformed * mask).astype(np.uint8)
+        if len(np.where(deformed == 0)[0]) >= 100:
+            return deformed, flow, mask
+
+
+def sff_noise_restated(img, det_size, rng):
+    """simu_sff/simuSFF.py:134-144 (works on a copy; the reference mutates its argument's box)."""
+    img = np.array(img, copy=True)
+    mask = np.ones_like(img)
+    mask[img == 0] = 0
+    ran = rng.uniform(0.4, 1.0)
+    ran_w = rng.randint(50, 200)
+    ran_h = rng.randint(50, 200)
+    px = rng.randint(0, det_size - ran_h)
+    py = rng.randint(0, det_size - ran_w)
+    box = img[px:px + ran_h, py:py + ran_w]
+    box = ran * (box - np.mean(img)) + np.mean(img)
+    img[px:px + ran_h, py:py + ran_w] = box
+    return np.multiply(img, mask)

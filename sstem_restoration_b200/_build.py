@@ -28,7 +28,7 @@ UNITS = [
     ("sepconv_k51_gi.cu", [], ""),
     ("sepconv_k51_tail.cu", [], ""),
     ("warp.cu", [], ""),
-    # ("sff_sim.cu", [], ""),
+    ("sff_sim.cu", [], ""),
     ("probe.cu", [], ""),
 ]
 NVCC_FLAGS = [

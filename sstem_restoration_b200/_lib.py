@@ -33,7 +33,7 @@ WARP_NEAREST = 1
 #: every symbol include/sstem_b200.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = (
     "sstem_sepconv_forward", "sstem_sepconv_backward", "sstem_interp_tail_forward", "sstem_interp_tail_backward",
-    "sstem_warp_forward", "sstem_image_warp",
+    "sstem_warp_forward", "sstem_image_warp", "sstem_sff_degrade", "sstem_sff_contrast",
     "sstem_fp32_peak_probe", "sstem_launch_count", "sstem_abi_version", "sstem_error_string",
 )
 
@@ -70,6 +70,10 @@ def load() -> ctypes.CDLL:
         lib.sstem_warp_forward.restype = ctypes.c_int
         lib.sstem_image_warp.argtypes = [_c_p, _c_i32, _c_p, _c_p, _c_p, _c_i64, _c_i64, _c_i64, _c_i64, _c_i32, _c_p]
         lib.sstem_image_warp.restype = ctypes.c_int
+        lib.sstem_sff_degrade.argtypes = [_c_p] * 6 + [_c_i64] * 3 + [_c_p]
+        lib.sstem_sff_degrade.restype = ctypes.c_int
+        lib.sstem_sff_contrast.argtypes = [_c_p] * 3 + [_c_i64] * 5 + [_c_p]
+        lib.sstem_sff_contrast.restype = ctypes.c_int
         lib.sstem_fp32_peak_probe.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
         lib.sstem_fp32_peak_probe.restype = ctypes.c_int
         lib.sstem_launch_count.argtypes = []

@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <stdlib.h>
+#include <type_traits>
 
 namespace sstem {
 
@@ -280,21 +281,56 @@ warp_torch_tma_kernel(const __grid_constant__ CUtensorMap map_fx, const __grid_c
     const int64_t plane = (int64_t)H * W;
     float* obase = out + (int64_t)b * CT * plane;
     if (fits) {
-        mbar_wait(&bar[1], 0);
+        // word offsets of the four taps of each pixel inside one channel plane of the window, and the
+        // pixel's offset inside one output plane: computed once, shared by all channels
+        int a00[4], a01[4], a10[4], a11[4];
+        unsigned ooff[4];
+        bool ok[4];
+        float2 wa2[2], wb2[2], wc2[2], wd2[2];          // pixels (0,1) and (2,3) side by side for the packed FP32 ops
 #pragma unroll
-        for (int c = 0; c < CT; ++c) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float* sp = s_im + c * cstride + offa[q];
-                const int dy = dys[q] * pitch;
-                const float Ia = sp[0], Ib = sp[dy], Ic = sp[dxs[q]], Id = sp[dy + dxs[q]];
-                float r = __fadd_rn(__fmul_rn(wa[q], Ia), __fmul_rn(wb[q], Ib));
-                r = __fadd_rn(r, __fmul_rn(wc[q], Ic));
-                r = __fadd_rn(r, __fmul_rn(wd[q], Id));
-                const int i = i0 + warp + WT_HALF * (q >> 1), j = j00 + lane + 32 * (q & 1);
-                if (i < H && j < W) __stcs(obase + c * plane + (int64_t)i * W + j, r);
-            }
+        for (int q = 0; q < 4; ++q) {
+            a00[q] = offa[q];
+            a01[q] = offa[q] + dxs[q];
+            a10[q] = offa[q] + dys[q] * pitch;
+            a11[q] = a10[q] + dxs[q];
+            const int i = i0 + warp + WT_HALF * (q >> 1), j = j00 + lane + 32 * (q & 1);
+            ok[q] = i < H && j < W;
+            ooff[q] = (unsigned)(i * W + j);
         }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            wa2[h] = make_float2(wa[2 * h], wa[2 * h + 1]); wb2[h] = make_float2(wb[2 * h], wb[2 * h + 1]);
+            wc2[h] = make_float2(wc[2 * h], wc[2 * h + 1]); wd2[h] = make_float2(wd[2 * h], wd[2 * h + 1]);
+        }
+        mbar_wait(&bar[1], 0);
+        // the channel stride is a compile-time constant inside each branch, so every LDS below is
+        // [register + immediate]: no integer work per load
+        auto blend = [&](auto cstride_tag) {
+            constexpr int CS = decltype(cstride_tag)::value;
+#pragma unroll
+            for (int c = 0; c < CT; ++c) {
+                const float* sc = s_im + c * CS;
+                float* oc = obase + c * plane;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int q0 = 2 * h, q1 = 2 * h + 1;
+                    const float2 Ia = make_float2(sc[a00[q0]], sc[a00[q1]]), Ib = make_float2(sc[a10[q0]], sc[a10[q1]]);
+                    const float2 Ic = make_float2(sc[a01[q0]], sc[a01[q1]]), Id = make_float2(sc[a11[q0]], sc[a11[q1]]);
+                    // image_warp_torch.py:93, per component: ((wa*Ia + wb*Ib) + wc*Ic) + wd*Id without
+                    // contraction.  The products are packed (FMUL2); the sums stay scalar because ptxas 12.9
+                    // fuses mul.rn.f32x2 + add.rn.f32x2 into FFMA2 despite the .rn (even with -fmad=false).
+                    const float2 pa = __fmul2_rn(wa2[h], Ia), pb = __fmul2_rn(wb2[h], Ib);
+                    const float2 pc = __fmul2_rn(wc2[h], Ic), pd = __fmul2_rn(wd2[h], Id);
+                    const float rx = __fadd_rn(__fadd_rn(__fadd_rn(pa.x, pb.x), pc.x), pd.x);
+                    const float ry = __fadd_rn(__fadd_rn(__fadd_rn(pa.y, pb.y), pc.y), pd.y);
+                    if (ok[q0]) __stcs(oc + ooff[q0], rx);
+                    if (ok[q1]) __stcs(oc + ooff[q1], ry);
+                }
+            }
+        };
+        if (small) blend(std::integral_constant<int, WT_SH * WT_SW>{});
+        else if (mid) blend(std::integral_constant<int, WT_MH * WT_MW>{});
+        else blend(std::integral_constant<int, WT_BH * WT_BW>{});
     } else {
         // taps spread beyond the window: gather from global memory (zero outside the image)
 #pragma unroll 1

@@ -67,6 +67,11 @@ def gen_flow_cases():
     }
 
 
+def simu_sff_cases():
+    """name -> (patch size, section index of synth.em_section, random.seed) for simuSFF.degradation + noise."""
+    return {"p256_seed555": (256, 3, 555), "p256_seed1": (256, 4, 1), "p300_seed77": (300, 5, 77)}
+
+
 def sepconv_cases():
     """name -> dict(B, C, H, W, seed, scale): seeded sepconv inputs (K = 51)."""
     return {

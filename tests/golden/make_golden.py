@@ -10,7 +10,11 @@ kernels (GPU) and require bit-equality.  Reference functions exercised:
   * sff_scripts_unfolding/utils/image_warp_torch.py:5-113 SpatialTransformation
   * simu_sff/flow_synthesis.py:13-83                      gen_line, gen_flow
     (imported with a stub `matplotlib` because flow_synthesis.py:6 imports pyplot)
+  * simu_sff/simuSFF.py:96-144                            degradation, noise
+    (imported with stub `matplotlib` / `skimage` modules: simuSFF.py:10-11 and flow_display.py:2
+    import them for PNG I/O and flow colouring only)
 """
+import hashlib
 import importlib.util
 import os
 import sys
@@ -77,6 +81,31 @@ def main():
         out[name + "_mask"] = mask.astype(np.uint8)
     np.savez_compressed(os.path.join(HERE, "gen_flow_ref.npz"), **out)
     print("gen_flow cases:", [k for k in out if k.endswith("_flow")])
+
+    # ---- simuSFF.degradation + noise (the reference's CPU-runnable config 1) -------------
+    import random
+    for name in ("skimage", "skimage.io"):
+        if name not in sys.modules:
+            try:
+                __import__(name)
+            except Exception:
+                sys.modules[name] = types.ModuleType(name)
+    if not hasattr(sys.modules["skimage"], "io"):
+        sys.modules["skimage"].io = sys.modules["skimage.io"]
+    ref_sim = _load(os.path.join(REF, "simu_sff", "simuSFF.py"), "ref_simuSFF", extra_path=os.path.join(REF, "simu_sff"))
+    from sstem_restoration_b200 import synth
+    out = {}
+    for name, (size, index, seed) in cases.simu_sff_cases().items():
+        img = synth.em_section(size, size, index)
+        random.seed(seed)
+        deformed, flow, mask = ref_sim.degradation(img, size)
+        out[name + "_deformed"] = deformed
+        # the float32 flow is 0.5-0.7 MB per case: the fixture keeps its SHA-256 (bit-equality is all that is tested)
+        out[name + "_flow_sha256"] = np.frombuffer(hashlib.sha256(np.ascontiguousarray(flow).tobytes()).digest(), np.uint8)
+        out[name + "_mask"] = np.packbits(mask.astype(np.uint8))
+        out[name + "_noise"] = ref_sim.noise(deformed.copy(), size)
+    np.savez_compressed(os.path.join(HERE, "simu_sff_ref.npz"), **out)
+    print("simuSFF cases:", {k: v.shape for k, v in out.items() if k.endswith("_noise")})
 
 
 if __name__ == "__main__":

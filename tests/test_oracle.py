@@ -147,3 +147,22 @@ def test_interp_tail_grads_match_autograd_f64():
     torch.mean(y, dim=1, keepdim=True).backward(torch.from_numpy(g).double())
     for got, tt in zip(oracle.interp_tail_grads_f64(g, i1, i2, *taps), t):
         assert float(np.abs(got - tt.grad.numpy()).max()) <= 1e-6
+
+
+# ------------------------------------------------------------------ SFF simulation (config 1) vs reference outputs
+@pytest.mark.parametrize("name", list(cases.simu_sff_cases()))
+def test_simu_sff_restatement_matches_reference_bitwise(golden_dir, name):
+    """oracle.sff_degradation_restated / sff_noise_restated against simu_sff/simuSFF.py:96-144 run by
+    tests/golden/make_golden.py with the same random.seed."""
+    import hashlib
+    import random
+    from sstem_restoration_b200 import synth
+    ref = np.load(os.path.join(golden_dir, "simu_sff_ref.npz"))
+    size, index, seed = cases.simu_sff_cases()[name]
+    img = synth.em_section(size, size, index)
+    rng = random.Random(seed)
+    deformed, flow, mask = oracle.sff_degradation_restated(img, size, rng)
+    assert np.array_equal(deformed, ref[name + "_deformed"])
+    assert hashlib.sha256(np.ascontiguousarray(flow).tobytes()).digest() == ref[name + "_flow_sha256"].tobytes()
+    assert np.array_equal(np.packbits(mask.astype(np.uint8)), ref[name + "_mask"])
+    assert np.array_equal(oracle.sff_noise_restated(deformed, size, rng), ref[name + "_noise"])
