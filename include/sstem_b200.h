@@ -216,6 +216,28 @@ int sstem_sff_contrast(uint8_t* img, const int64_t* stats, const double* params,
                        int64_t batch, int64_t h, int64_t w, int64_t max_box_h, int64_t max_box_w, void* stream);
 
 /*
+ * Network input from two uint8 sections, on the device -- sff_scripts_interp/inference.py:69-83:
+ *   inputs = concat(repeat(section[k-1], 3), repeat(section[k+1], 3)).astype(float32) / 255.0,
+ *   zero-padded by `pad` on every side (F.pad(inputs, (PAD,)*4)).
+ *   section_prev, section_next  [batch, h, w] uint8
+ *   inputs                      [batch, 6, h + 2*pad, w + 2*pad] float32
+ * Bit-equal to the numpy expression; only the uint8 sections have to cross PCIe.
+ */
+int sstem_sections_to_input(const uint8_t* section_prev, const uint8_t* section_next, float* inputs,
+                            int64_t batch, int64_t h, int64_t w, int32_t pad, void* stream);
+
+/*
+ * Network output to a uint8 section -- sff_scripts_interp/inference.py:84-88:
+ *   section = (F.pad(pred, (-PAD,)*4) * 255).astype(np.uint8)
+ *   pred     [batch, 1, h + 2*pad, w + 2*pad] float32
+ *   section  [batch, h, w] uint8
+ * Values outside [0, 256) convert as C does through int32 (what numpy does on x86-64); NaN / |v| >=
+ * 2^31 are unspecified there as well.
+ */
+int sstem_prediction_to_u8(const float* pred, uint8_t* section, int64_t batch, int64_t h, int64_t w,
+                           int32_t pad, void* stream);
+
+/*
  * FP32 FMA-pipe probe: runs a register-resident FFMA loop on every SM of the
  * current device and returns the sustained rate in TFLOP/s (2 flop per FMA).
  * bench.py uses it as the measured denominator of the sepconv roofline

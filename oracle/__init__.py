@@ -344,3 +344,21 @@ def sff_noise_restated(img, det_size, rng):
     box = ran * (box - np.mean(img)) + np.mean(img)
     img[px:px + ran_h, py:py + ran_w] = box
     return np.multiply(img, mask)
+
+
+# --------------------------------------------------------------------------- stack pre/post-processing
+def sections_to_input_restated(img1, img2, pad):
+    """sff_scripts_interp/inference.py:69-83 on numpy (F.pad with zeros == np.pad constant)."""
+    img1 = np.repeat(np.asarray(img1)[np.newaxis, :, :], 3, 0)
+    img2 = np.repeat(np.asarray(img2)[np.newaxis, :, :], 3, 0)
+    inputs = np.concatenate([img1, img2], axis=0)[np.newaxis]
+    inputs = inputs.astype(np.float32) / 255.0
+    return np.pad(inputs, ((0, 0), (0, 0), (pad, pad), (pad, pad)))
+
+
+def prediction_to_uint8_restated(pred, pad):
+    """inference.py:84-88: negative pad = crop, squeeze, * 255, astype(uint8)."""
+    pred = np.asarray(pred, dtype=np.float32)
+    if pad:
+        pred = pred[..., pad:-pad, pad:-pad]
+    return (np.squeeze(pred) * 255).astype(np.uint8)

@@ -29,6 +29,7 @@ UNITS = [
     ("sepconv_k51_tail.cu", [], ""),
     ("warp.cu", [], ""),
     ("sff_sim.cu", [], ""),
+    ("stack_io.cu", [], ""),
     ("probe.cu", [], ""),
 ]
 NVCC_FLAGS = [

@@ -1,0 +1,102 @@
+// Stack pre/post-processing either side of the interpolation path, on the device, so only uint8
+// sections cross PCIe -- SURVEY.md section 8f, N4.
+//
+//  * sections_to_input_kernel: sff_scripts_interp/inference.py:69-83 --
+//        img1 = np.repeat(section[k-1][None], 3, 0); img2 likewise for k+1
+//        inputs = np.concatenate([img1, img2], 0)[None].astype(np.float32) / 255.0
+//        inputs = F.pad(inputs, (PAD, PAD, PAD, PAD))                  (zeros)
+//    uint8 [B,H,W] x 2  ->  float32 [B,6,H+2P,W+2P]: 2 B read, 24 B written per pixel (HBM-bound
+//    streaming write; the host path uploads those 24 B per pixel over PCIe instead).
+//  * prediction_to_u8_kernel: inference.py:84-88 --
+//        pred = F.pad(pred, (-PAD, -PAD, -PAD, -PAD)); (pred * 255).astype(np.uint8)
+//    float32 [B,1,H+2P,W+2P] -> uint8 [B,H,W].
+// Both are bit-equal to the numpy expressions (IEEE division by 255, float32 product, C truncation).
+#include "common.cuh"
+
+namespace sstem {
+namespace {
+
+// one thread = 4 consecutive columns of one padded output row, all six channel planes
+__global__ void __launch_bounds__(256)
+sections_to_input_kernel(const uint8_t* __restrict__ sec_a, const uint8_t* __restrict__ sec_b,
+                         float* __restrict__ out, int H, int W, int pad) {
+    const int OW = W + 2 * pad, OH = H + 2 * pad;
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y;
+    const int64_t b = blockIdx.z;
+    if (x0 >= OW) return;
+    const int sy = y - pad;
+    float va[4], vb[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int sx = x0 + q - pad;
+        const bool in = (unsigned)sy < (unsigned)H && (unsigned)sx < (unsigned)W;
+        const int64_t o = (b * H + (in ? sy : 0)) * (int64_t)W + (in ? sx : 0);
+        va[q] = in ? __fdiv_rn((float)__ldg(sec_a + o), 255.0f) : 0.f;
+        vb[q] = in ? __fdiv_rn((float)__ldg(sec_b + o), 255.0f) : 0.f;
+    }
+    const int64_t plane = (int64_t)OH * OW;
+    float* row = out + b * 6 * plane + (int64_t)y * OW + x0;
+    const bool vec = (x0 + 4 <= OW) && ((reinterpret_cast<uintptr_t>(row) & 15u) == 0) && ((plane & 3) == 0);
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+        const float* v = c < 3 ? va : vb;               // channels 0-2: section k-1, 3-5: section k+1
+        float* dst = row + c * plane;
+        if (vec) __stcs(reinterpret_cast<float4*>(dst), make_float4(v[0], v[1], v[2], v[3]));
+        else
+            for (int q = 0; q < 4 && x0 + q < OW; ++q) dst[q] = v[q];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+prediction_to_u8_kernel(const float* __restrict__ pred, uint8_t* __restrict__ out, int H, int W, int pad) {
+    const int OW = W + 2 * pad, OH = H + 2 * pad;
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y;
+    const int64_t b = blockIdx.z;
+    if (x0 >= W) return;
+    const float* src = pred + (b * OH + y + pad) * (int64_t)OW + pad + x0;
+    uint8_t r[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float v = __fmul_rn(__ldcs(src + min(q, W - 1 - x0)), 255.0f);
+        r[q] = (uint8_t)(int)v;                         // astype(np.uint8): C truncation (through int32)
+    }
+    uint8_t* dst = out + (b * H + y) * (int64_t)W + x0;
+    if (x0 + 4 <= W && (reinterpret_cast<uintptr_t>(dst) & 3u) == 0) *reinterpret_cast<uchar4*>(dst) = make_uchar4(r[0], r[1], r[2], r[3]);
+    else
+        for (int q = 0; q < 4 && x0 + q < W; ++q) dst[q] = r[q];
+}
+
+}  // namespace
+}  // namespace sstem
+
+using namespace sstem;
+
+extern "C" int sstem_sections_to_input(const uint8_t* section_prev, const uint8_t* section_next, float* inputs,
+                                       int64_t B, int64_t H, int64_t W, int32_t pad, void* stream) {
+    if (!section_prev || !section_next || !inputs) return SSTEM_E_NULL;
+    if (B <= 0 || H <= 0 || W <= 0 || pad < 0 || B > 65535 || H + 2 * (int64_t)pad > 65535 || W + 2 * (int64_t)pad > INT32_MAX / 2)
+        return SSTEM_E_SHAPE;
+    if (!aligned4(inputs)) return SSTEM_E_ALIGN;
+    DeviceGuard guard(inputs);
+    if (guard.err) return guard.err;
+    const int64_t OW = W + 2 * pad, OH = H + 2 * pad;
+    dim3 grid((unsigned)((OW + 1023) / 1024), (unsigned)OH, (unsigned)B);
+    sections_to_input_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(section_prev, section_next, inputs, (int)H, (int)W, (int)pad);
+    count_launch();
+    return finish_launch();
+}
+
+extern "C" int sstem_prediction_to_u8(const float* pred, uint8_t* section, int64_t B, int64_t H, int64_t W, int32_t pad,
+                                      void* stream) {
+    if (!pred || !section) return SSTEM_E_NULL;
+    if (B <= 0 || H <= 0 || W <= 0 || pad < 0 || B > 65535 || H > 65535 || W + 2 * (int64_t)pad > INT32_MAX / 2) return SSTEM_E_SHAPE;
+    if (!aligned4(pred)) return SSTEM_E_ALIGN;
+    DeviceGuard guard(section);
+    if (guard.err) return guard.err;
+    dim3 grid((unsigned)((W + 1023) / 1024), (unsigned)H, (unsigned)B);
+    prediction_to_u8_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pred, section, (int)H, (int)W, (int)pad);
+    count_launch();
+    return finish_launch();
+}

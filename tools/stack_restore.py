@@ -5,7 +5,9 @@
 
 Target k (interior section) is interpolated from sections k-1 and k+1 exactly as the reference's
 tail does (sff_scripts_interp/inference.py:69-89 -> model_interp.py:90-97): two sepconv calls on the
-replicate-padded neighbours + add + channel mean; the degraded section k itself is flow-warped
+replicate-padded neighbours + add + channel mean -- by default as ONE launch (interpolation_tail),
+with uint8 sections on the wire (sections_to_input / prediction_to_uint8 replace inference.py:69-88's
+host-side /255, x3 replicate and *255 cast); the degraded section k itself is flow-warped
 (sff_scripts_fusion/inference.py:149-150).  Taps and flows are synthetic (the KPN / flow net are out
 of scope).  Ranks own contiguous target ranges (shard.shard_range), never communicate while
 computing, and the restored sections are gathered to rank 0 at the end (the path's only collective).
@@ -30,6 +32,9 @@ def main():
     ap.add_argument("--sections", type=int, default=20)
     ap.add_argument("--size", type=int, default=2048)
     ap.add_argument("--gray", default="detect", choices=["off", "assert", "detect"])
+    ap.add_argument("--unfused", action="store_true",
+                    help="float sections on the wire and the reference's op-by-op tail (2 pads + 2 sepconvs + add + mean) "
+                         "instead of uint8 sections + sections_to_input + interpolation_tail + prediction_to_uint8")
     args = ap.parse_args()
     rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     torch.cuda.set_device(local)
@@ -43,24 +48,38 @@ def main():
     pkg.set_gray_replicated(args.gray)
     sep = pkg.SeparableConvolution.apply
     warp = pkg.SpatialTransformation(True)
+    pad = torch.nn.ReplicationPad2d(25)
     gen = torch.Generator(device=dev).manual_seed(4321 + rank)
     # synthetic taps / flow, reused for every pair (their values do not affect speed)
     taps = [torch.softmax(torch.randn((1, 51, H, W), device=dev, generator=gen), 1) for _ in range(4)]
     flow_np, _ = synth.random_fold_flow(H, W, 555)
     flow = torch.from_numpy(np.ascontiguousarray(flow_np.transpose(2, 0, 1))[None]).to(dev).permute(0, 2, 3, 1)
-    base = torch.from_numpy(synth.section_to_input(synth.em_section(min(H, 1024), min(W, 1024), 0))).to(dev)
+    # the stack as it sits on the host: uint8 sections in pinned memory (a stand-in for decoded PNGs)
+    tile = synth.em_section(min(H, 1024), min(W, 1024), 0)
+    base = torch.from_numpy(np.tile(tile, (H // tile.shape[0], W // tile.shape[1]))).pin_memory()
+    need = sorted({k for t in targets[lo:hi] for k in t})
+    host = {k: torch.roll(base, shifts=7 * k, dims=1).pin_memory() for k in need}
 
-    def section(idx):                                   # a cheap deterministic stand-in for PNG decode
-        reps = (1, (H + 50 + base.shape[1] - 1) // base.shape[1], (W + 50 + base.shape[2] - 1) // base.shape[2])
-        return (base.repeat(*reps)[:, : H + 50, : W + 50].roll(idx * 7, 2)[None]).contiguous()
+    def restore(ka, k, kb):
+        """One target: sections k-1 / k+1 -> interpolated section k; section k itself -> flow-corrected; blend."""
+        up = {i: host[i].to(dev, non_blocking=True) for i in (ka, k, kb)}                 # 1 byte per pixel over PCIe
+        x = pkg.sections_to_input(up[ka], up[kb], 0)                                        # [1,6,H,W] float, /255, x3
+        if args.unfused:
+            y = sep(pad(x[:, 3:6]), taps[0], taps[1]) + sep(pad(x[:, :3]), taps[2], taps[3])
+            interp = torch.mean(y, dim=1, keepdim=True)
+        else:
+            interp = pkg.interpolation_tail(x[:, :3], x[:, 3:6], taps[2], taps[3], taps[0], taps[1])
+        xk = pkg.sections_to_input(up[k], up[k], 0)[:, :3].contiguous()
+        warped = warp(xk, flow)                                                             # correction-module warp of section k
+        return pkg.prediction_to_uint8(0.5 * (interp + warped[:, :1]), 0)                   # [1,H,W] uint8
 
-    restored = torch.empty((hi - lo, 1, H, W), device=dev)
+    restored = torch.empty((hi - lo, H, W), dtype=torch.uint8, device=dev)
     with torch.no_grad():                               # warm-up: first-launch setup, allocator, NCCL communicator
-        i1 = section(0)
-        _ = torch.mean(sep(i1, taps[0], taps[1]) + sep(i1, taps[2], taps[3]), dim=1, keepdim=True)
-        _ = warp(i1[:, :, 25:-25, 25:-25].contiguous(), flow)
+        if hi > lo:
+            restore(*targets[lo])
         if world > 1:
-            shard.gather_sections(torch.zeros((1, 1, 8, 8), device=dev).expand(shard.shard_range(world, rank, world)[1] - shard.shard_range(world, rank, world)[0], 1, 8, 8).contiguous(), world, dst=0)
+            n_w = shard.shard_range(world, rank, world)
+            shard.gather_sections(torch.zeros((n_w[1] - n_w[0], 8, 8), dtype=torch.uint8, device=dev), world, dst=0)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -68,12 +87,8 @@ def main():
     n0 = pkg.launch_count()
     e0.record()
     with torch.no_grad():
-        for n, (ka, k, kb) in enumerate(targets[lo:hi]):
-            i1, i2, ik = section(ka), section(kb), section(k)
-            y = sep(i2, taps[0], taps[1]) + sep(i1, taps[2], taps[3])
-            interp = torch.mean(y, dim=1, keepdim=True)
-            warped = warp(ik[:, :, 25:-25, 25:-25].contiguous(), flow)          # correction-module warp of section k
-            restored[n] = 0.5 * (interp[0] + warped[0, :1])
+        for n, t in enumerate(targets[lo:hi]):
+            restored[n] = restore(*t)[0]
     full = shard.gather_sections(restored, len(targets), dst=0) if world > 1 else restored
     e1.record()
     torch.cuda.synchronize()
@@ -85,7 +100,9 @@ def main():
         print(json.dumps({"workload": f"stack restoration, {args.sections} sections {H}x{W}, {len(targets)} targets", "n_gpus": world,
                           "seconds": round(t, 4), "sections_per_s": round(len(targets) / t, 2),
                           "mpix_per_s": round(len(targets) * H * W / t / 1e6, 1), "gray_mode": args.gray,
-                          "gathered": list(full.shape), "kernel_launches_rank0": pkg.launch_count() - n0}))
+                          "path": "unfused float" if args.unfused else "uint8 wire + fused tail",
+                          "gathered": list(full.shape), "gathered_dtype": str(full.dtype),
+                          "kernel_launches_rank0": pkg.launch_count() - n0}))
     if world > 1:
         dist.destroy_process_group()
 
