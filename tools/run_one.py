@@ -1,4 +1,5 @@
-"""Runs a few launches of one op for profiling under ncu.  usage: run_one.py <fwd|bwd|gi|warp> B C H W [reps]"""
+"""Runs a few launches of one op for profiling under ncu.  usage: run_one.py <fwd|bwd|gi|warp|tail|tailbwd> B C H W [reps]
+(tail / tailbwd: fused interpolation tail, gray-replicated frames asserted when GRAY=1)"""
 import os
 import sys
 import torch
@@ -25,6 +26,20 @@ if op == "warp":
     m = pkg.SpatialTransformation(True)
     for _ in range(reps):
         m(im, fl)
+elif op in ("tail", "tailbwd"):
+    f1 = torch.rand((B, 1, H, W), device=dev).expand(B, C, H, W).contiguous()
+    f2 = torch.rand((B, 1, H, W), device=dev).expand(B, C, H, W).contiguous()
+    taps = [torch.softmax(torch.randn((B, K, H, W), device=dev), 1) for _ in range(4)]
+    out = torch.empty((B, 1, H, W), device=dev)
+    grads = [torch.empty_like(t) for t in taps]
+    g = torch.randn((B, 1, H, W), device=dev)
+    flag = 2 if os.environ.get("GRAY", "1") == "1" else 0
+    for _ in range(reps):
+        if op == "tail":
+            lib.sstem_interp_tail_forward(f1.data_ptr(), f2.data_ptr(), C * H * W, *[t.data_ptr() for t in taps], out.data_ptr(), B, C, H, W, K, flag, st)
+        else:
+            lib.sstem_interp_tail_backward(g.data_ptr(), f1.data_ptr(), f2.data_ptr(), C * H * W, *[t.data_ptr() for t in taps],
+                                           *[t.data_ptr() for t in grads], B, C, H, W, K, flag, st)
 else:
     inp = torch.rand((B, C, H + 50, W + 50), device=dev)
     v = torch.softmax(torch.randn((B, K, H, W), device=dev), 1)
