@@ -55,7 +55,11 @@ constexpr int VDEPTH = 8;                  // steps of vertical taps in flight p
 #endif
 #ifndef SSTEM_FWD_NPRE
 #define SSTEM_FWD_NPRE 13                  // taps of the next row (channel 0) preloaded during the current step;
-                                           // only used by the 3-channel kernel (measured: +2 % there, -5 % at C = 1)
+                                           // 3-channel kernel (measured: +2 % there; 13 at C = 1 costs 5 %)
+#endif
+#ifndef SSTEM_FWD_NPRE1
+#define SSTEM_FWD_NPRE1 4                  // the same for the one- / two-channel kernels and the fused tail (measured:
+                                           // gray x3 forward +5 %, tail +0.4 %; 8 is no better)
 #endif
 #ifndef SSTEM_BWD_NPRE
 #define SSTEM_BWD_NPRE 7                   // taps of the next row preloaded during the current step
@@ -309,7 +313,7 @@ __device__ __forceinline__ void fwd_step(const float* __restrict__ prow0, bool n
                                          const float2 (&h2)[R / 2][Geo<G, R>::NT], const float2 (&v2)[R / 2],
                                          float2 (&acc)[CC][R / 2], float (&pre)[SSTEM_FWD_NPRE + 1]) {
     using Gm = Geo<G, R>;
-    constexpr int NPRE = (CC >= 3) ? SSTEM_FWD_NPRE : 0;                 // channel 0's first taps were loaded during the previous step
+    constexpr int NPRE = (CC >= 3) ? SSTEM_FWD_NPRE : SSTEM_FWD_NPRE1;   // channel 0's first taps were loaded during the previous step
 #pragma unroll
     for (int c = 0; c < CC; ++c) {
         const float* prow = prow0 + c * Gm::ROWS * Gm::PITCH;
@@ -392,7 +396,7 @@ sepconv_fwd_k51_kernel(const float* __restrict__ in, const float* __restrict__ v
     };
     float pre[SSTEM_FWD_NPRE + 1];
 #pragma unroll
-    for (int t = 0; t < ((CC >= 3) ? SSTEM_FWD_NPRE : 0); ++t) pre[t] = prow[G * t];
+    for (int t = 0; t < ((CC >= 3) ? SSTEM_FWD_NPRE : SSTEM_FWD_NPRE1); ++t) pre[t] = prow[G * t];
 #define SSTEM_FWD_EDGE_STEP(S)                                                     \
     if ((S) < R - 1 || ((S) >= K51 && (S) < Gm::ROWS)) {                           \
         advance();                                                                 \
@@ -883,8 +887,11 @@ struct TailFrames {                                     // indexed by the frame 
     const float* h[2];
 };
 
+#ifndef SSTEM_TAIL_MINB
+#define SSTEM_TAIL_MINB 2
+#endif
 template <int G, int R, bool VEC>
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(128, SSTEM_TAIL_MINB)
 interp_tail_fwd_k51_kernel(const __grid_constant__ TailFrames fa, int64_t frame_bstride, int cs, int nplanes,
                            float* __restrict__ out, float scale, int H, int W) {
     using Gm = Geo<G, R>;
@@ -932,7 +939,9 @@ interp_tail_fwd_k51_kernel(const __grid_constant__ TailFrames fa, int64_t frame_
             vr.issue();
             vr.read(vnext);
         };
-        float pre[SSTEM_FWD_NPRE + 1];                  // unused at one channel
+        float pre[SSTEM_FWD_NPRE + 1];
+#pragma unroll
+        for (int t = 0; t < SSTEM_FWD_NPRE1; ++t) pre[t] = prow[G * t];
 #define SSTEM_TAIL_EDGE_STEP(S)                                                    \
     if ((S) < R - 1 || ((S) >= K51 && (S) < Gm::ROWS)) {                           \
         advance();                                                                 \

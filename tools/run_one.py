@@ -26,6 +26,13 @@ if op == "warp":
     m = pkg.SpatialTransformation(True)
     for _ in range(reps):
         m(im, fl)
+elif op == "sff":
+    from sstem_restoration_b200 import sff_sim, synth
+    img = torch.randint(0, 256, (B, H, W), dtype=torch.uint8, device=dev)
+    k, b = synth.gen_line([0, W // 3], [H, 2 * W // 3])
+    prm = [sff_sim.fold_line_params(k, b, 12, 60, 0.05)] * B
+    for _ in range(reps):
+        sff_sim.gen_flow_warp(img, prm, want_flow=False, want_mask=False)
 elif op in ("tail", "tailbwd"):
     f1 = torch.rand((B, 1, H, W), device=dev).expand(B, C, H, W).contiguous()
     f2 = torch.rand((B, 1, H, W), device=dev).expand(B, C, H, W).contiguous()
