@@ -196,11 +196,17 @@ int sstem_image_warp(const void* im, int32_t pix_type, const float* flow,
  *            Python's math module (passed in so the device never re-derives a libm result)
  *   out      [batch, h, w] uint8
  *   flow_out [batch, h, w, 2] float32 or NULL;  mask_out [batch, h, w] uint8 (0/1) or NULL
+ *   flow2_out [batch, h, w, 2] float32 or NULL: the second flow of the training data providers'
+ *            gen_flow variant (sff_scripts_unfolding/utils/flow_synthesis.py:44-61 -- displacement kept
+ *            beyond fold_width, opposite sign; the label of sff_scripts_unfolding/data/data_provider.py:225-239)
  *   stats    DEVICE [batch][2] int64, overwritten: number of zero pixels of `out` (the accept test
- *            of simuSFF.py:125-130) and the sum of its pixels (np.mean for sstem_sff_contrast)
+ *            of simuSFF.py:125-130) and the sum of its pixels (np.mean for sstem_sff_contrast), both
+ *            taken over the pixels at least `stats_border` away from the image border (0 for simuSFF;
+ *            the data providers count on the centre crop, data_provider.py:231-238)
  */
 int sstem_sff_degrade(const uint8_t* img, const double* params, uint8_t* out, float* flow_out,
-                      uint8_t* mask_out, int64_t* stats, int64_t batch, int64_t h, int64_t w, void* stream);
+                      float* flow2_out, uint8_t* mask_out, int64_t* stats,
+                      int64_t batch, int64_t h, int64_t w, int64_t stats_border, void* stream);
 
 /*
  * Regional-contrast step of simuSFF.py:134-144 (`noise`), in place on the image sstem_sff_degrade

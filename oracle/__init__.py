@@ -346,6 +346,33 @@ def sff_noise_restated(img, det_size, rng):
     return np.multiply(img, mask)
 
 
+def provider_degradation_restated(img, crop_size, offset, rng, line_width_max=50):
+    """Provider.degradation of the training data providers restated on numpy
+    (sff_scripts_unfolding/data/data_provider.py:180-245; fusion: line_width_max = 20).
+    -> (deformed uint8 centre crop, flow2 float32 centre crop)."""
+    from sstem_restoration_b200 import synth
+    while True:
+        height = width = crop_size
+        line_width = rng.randint(5, line_width_max)
+        fold_width = rng.randint(line_width + 1, 80)
+        k1 = rng.randint(1, 4)
+        k2 = rng.randint(1, 4)
+        while k1 == k2:
+            k2 = rng.randint(1, 4)
+        pts = []
+        for side in (k1, k2):
+            x = rng.randint(1, (width if side in (1, 3) else height) - 1)
+            pts.append({1: [0, x], 2: [x, width], 3: [height, x], 4: [x, 0]}[side])
+        dis_k = rng.uniform(0.00001, 0.1)
+        k, b = synth.gen_line(pts[0], pts[1])
+        flow, flow2, mask = synth.gen_flow(height, width, k, b, line_width, fold_width, dis_k, two_flows=True)
+        deformed = (image_warp_restated(img, flow, mode="bilinear") * mask).astype(np.uint8)
+        deformed = deformed[offset:-offset, offset:-offset]
+        flow2 = flow2[offset:-offset, offset:-offset]
+        if len(np.where(deformed == 0)[0]) >= 100:
+            return deformed, flow2
+
+
 # --------------------------------------------------------------------------- stack pre/post-processing
 def sections_to_input_restated(img1, img2, pad):
     """sff_scripts_interp/inference.py:69-83 on numpy (F.pad with zeros == np.pad constant)."""

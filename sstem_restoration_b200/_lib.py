@@ -71,7 +71,7 @@ def load() -> ctypes.CDLL:
         lib.sstem_warp_forward.restype = ctypes.c_int
         lib.sstem_image_warp.argtypes = [_c_p, _c_i32, _c_p, _c_p, _c_p, _c_i64, _c_i64, _c_i64, _c_i64, _c_i32, _c_p]
         lib.sstem_image_warp.restype = ctypes.c_int
-        lib.sstem_sff_degrade.argtypes = [_c_p] * 6 + [_c_i64] * 3 + [_c_p]
+        lib.sstem_sff_degrade.argtypes = [_c_p] * 7 + [_c_i64] * 4 + [_c_p]
         lib.sstem_sff_degrade.restype = ctypes.c_int
         lib.sstem_sff_contrast.argtypes = [_c_p] * 3 + [_c_i64] * 5 + [_c_p]
         lib.sstem_sff_contrast.restype = ctypes.c_int

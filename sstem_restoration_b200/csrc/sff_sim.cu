@@ -25,7 +25,11 @@ struct FoldLine {                                       // one row of the params
 };
 
 // flow_synthesis.py:32-82 for pixel (row i, column j); returns the float32 flow and the 0/1 mask
-__device__ __forceinline__ void fold_flow_at(const FoldLine& p, int i, int j, float& fx, float& fy, bool& mask) {
+// (fx2, fy2): the second flow of the data providers' gen_flow variant
+// (sff_scripts_unfolding/utils/flow_synthesis.py:44-61 -- displacement kept beyond fold_width, opposite sign)
+template <bool FLOW2>
+__device__ __forceinline__ void fold_flow_at(const FoldLine& p, int i, int j, float& fx, float& fy, bool& mask,
+                                             float& fx2, float& fy2) {
     // dis = (k * pos_x - pos_y + b) / sqrt(k**2 + 1)
     const double dis = __ddiv_rn(__dadd_rn(__dsub_rn(__dmul_rn(p.k, (double)j), (double)i), p.b), p.norm);
     const double sign = dis > 0.0 ? 1.0 : (dis < 0.0 ? -1.0 : 0.0);
@@ -36,6 +40,14 @@ __device__ __forceinline__ void fold_flow_at(const FoldLine& p, int i, int j, fl
     const double dis_b = __dsub_rn(__dsub_rn(p.fold_width, p.line_width), __dmul_rn(dk, p.line_width));   // :49,57
     double s = __dadd_rn(__dmul_rn(dk, dis_abs), dis_b);                                                   // :58
     if (s < 0.0) s = 0.0;                               // :59
+    if (FLOW2) {
+        // unfolding flow_synthesis.py:48-49,58,62: s * mask_dis2 + dis_abs * (1 - mask_dis2), times (-sign)
+        const double s2 = !(dis_abs < p.fold_width) ? __dadd_rn(s, 0.0) : dis_abs;
+        const double d2 = __dmul_rn(s2, -sign);
+        const double dc2 = __dmul_rn(d2, p.cos_p), ds2 = __dmul_rn(d2, p.sin_p);
+        if (p.k > 0.0) { fx2 = __double2float_rn(dc2); fy2 = __double2float_rn(-ds2); }
+        else { fx2 = __double2float_rn(-dc2); fy2 = __double2float_rn(ds2); }
+    }
     // :60  s * mask_dis + dis_abs * (1 - mask_dis): one of the two products is exactly 0
     s = outside ? __dadd_rn(s, 0.0) : dis_abs;
     const double d = __dmul_rn(s, sign);                // :62
@@ -64,10 +76,13 @@ __device__ __forceinline__ uint8_t numpy_warp_u8(const uint8_t* __restrict__ im,
 
 constexpr int DG_TX = 64, DG_TY = 4, DG_PX = 4;         // block = 64 x 4 threads, 4 pixels along x per thread
 
+// `border`: pixels closer than this to the image border are left out of the statistics (the data
+// providers count zeros on the centre crop, data_provider.py:231-238); 0 for simuSFF.
+template <bool FLOW2>
 __global__ void __launch_bounds__(DG_TX * DG_TY)
 sff_degrade_kernel(const uint8_t* __restrict__ img, const double* __restrict__ params,
-                   uint8_t* __restrict__ out, float* __restrict__ flow_out, uint8_t* __restrict__ mask_out,
-                   unsigned long long* __restrict__ stats, int H, int W) {
+                   uint8_t* __restrict__ out, float* __restrict__ flow_out, float* __restrict__ flow2_out,
+                   uint8_t* __restrict__ mask_out, unsigned long long* __restrict__ stats, int H, int W, int border) {
     const int b = blockIdx.z;
     const int i = blockIdx.y * DG_TY + threadIdx.y;
     const int j0 = (blockIdx.x * DG_TX + threadIdx.x) * DG_PX;
@@ -78,16 +93,17 @@ sff_degrade_kernel(const uint8_t* __restrict__ img, const double* __restrict__ p
     unsigned zeros = 0, sum = 0;
     if (i < H && j0 < W) {
         uint8_t res[DG_PX], msk[DG_PX];
-        float fx[DG_PX], fy[DG_PX];
+        float fx[DG_PX], fy[DG_PX], fx2[DG_PX], fy2[DG_PX];
+        const bool row_counts = i >= border && i < H - border;
 #pragma unroll
         for (int q = 0; q < DG_PX; ++q) {
             const int j = min(j0 + q, W - 1);
             bool m;
-            fold_flow_at(p, i, j, fx[q], fy[q], m);
+            fold_flow_at<FLOW2>(p, i, j, fx[q], fy[q], m, fx2[q], fy2[q]);
             const uint8_t v = numpy_warp_u8(im, fx[q], fy[q], i, j, H, W);
             res[q] = m ? v : (uint8_t)0;                // (deformed * mask).astype(uint8)
             msk[q] = m ? 1 : 0;
-            if (j0 + q < W) { zeros += (res[q] == 0); sum += res[q]; }
+            if (j0 + q < W && row_counts && j0 + q >= border && j0 + q < W - border) { zeros += (res[q] == 0); sum += res[q]; }
         }
         const int64_t o = b * plane + (int64_t)i * W + j0;
         const bool full = (j0 + DG_PX <= W);
@@ -102,15 +118,17 @@ sff_degrade_kernel(const uint8_t* __restrict__ img, const double* __restrict__ p
             else
                 for (int q = 0; q < DG_PX && j0 + q < W; ++q) mask_out[o + q] = msk[q];
         }
-        if (flow_out) {
-            float* fo = flow_out + 2 * o;
+        auto store_flow = [&](float* base, const float (&ax)[DG_PX], const float (&ay)[DG_PX]) {
+            float* fo = base + 2 * o;
             if (full && ((reinterpret_cast<uintptr_t>(fo) & 15u) == 0)) {
-                __stcs(reinterpret_cast<float4*>(fo), make_float4(fx[0], fy[0], fx[1], fy[1]));
-                __stcs(reinterpret_cast<float4*>(fo) + 1, make_float4(fx[2], fy[2], fx[3], fy[3]));
+                __stcs(reinterpret_cast<float4*>(fo), make_float4(ax[0], ay[0], ax[1], ay[1]));
+                __stcs(reinterpret_cast<float4*>(fo) + 1, make_float4(ax[2], ay[2], ax[3], ay[3]));
             } else {
-                for (int q = 0; q < DG_PX && j0 + q < W; ++q) { fo[2 * q] = fx[q]; fo[2 * q + 1] = fy[q]; }
+                for (int q = 0; q < DG_PX && j0 + q < W; ++q) { fo[2 * q] = ax[q]; fo[2 * q + 1] = ay[q]; }
             }
-        }
+        };
+        if (flow_out) store_flow(flow_out, fx, fy);
+        if (FLOW2 && flow2_out) store_flow(flow2_out, fx2, fy2);
     }
     // zero count and pixel sum of image b: warp reduce, then one atomic pair per block
     zeros = __reduce_add_sync(0xffffffffu, zeros);
@@ -154,11 +172,13 @@ sff_contrast_kernel(uint8_t* __restrict__ img, const unsigned long long* __restr
 using namespace sstem;
 
 extern "C" int sstem_sff_degrade(const uint8_t* img, const double* params, uint8_t* out, float* flow_out,
-                                 uint8_t* mask_out, int64_t* stats, int64_t B, int64_t H, int64_t W, void* stream) {
+                                 float* flow2_out, uint8_t* mask_out, int64_t* stats, int64_t B, int64_t H, int64_t W,
+                                 int64_t stats_border, void* stream) {
     if (!img || !params || !out || !stats) return SSTEM_E_NULL;
     if (B <= 0 || H <= 0 || W <= 0 || B > 65535 || H * W > INT32_MAX) return SSTEM_E_SHAPE;
+    if (stats_border < 0 || 2 * stats_border >= H || 2 * stats_border >= W) return SSTEM_E_SHAPE;
     if ((reinterpret_cast<uintptr_t>(params) & 7u) || (reinterpret_cast<uintptr_t>(stats) & 7u)) return SSTEM_E_ALIGN;
-    if (flow_out && !aligned4(flow_out)) return SSTEM_E_ALIGN;
+    if ((flow_out && !aligned4(flow_out)) || (flow2_out && !aligned4(flow2_out))) return SSTEM_E_ALIGN;
     DeviceGuard guard(out);
     if (guard.err) return guard.err;
     cudaStream_t s = (cudaStream_t)stream;
@@ -167,8 +187,12 @@ extern "C" int sstem_sff_degrade(const uint8_t* img, const double* params, uint8
     dim3 block(DG_TX, DG_TY);
     dim3 grid((unsigned)((W + DG_TX * DG_PX - 1) / (DG_TX * DG_PX)), (unsigned)((H + DG_TY - 1) / DG_TY), (unsigned)B);
     if (grid.y > 65535) return SSTEM_E_SHAPE;
-    sff_degrade_kernel<<<grid, block, 0, s>>>(img, params, out, flow_out, mask_out,
-                                              reinterpret_cast<unsigned long long*>(stats), (int)H, (int)W);
+    if (flow2_out)
+        sff_degrade_kernel<true><<<grid, block, 0, s>>>(img, params, out, flow_out, flow2_out, mask_out,
+                                                        reinterpret_cast<unsigned long long*>(stats), (int)H, (int)W, (int)stats_border);
+    else
+        sff_degrade_kernel<false><<<grid, block, 0, s>>>(img, params, out, flow_out, flow2_out, mask_out,
+                                                         reinterpret_cast<unsigned long long*>(stats), (int)H, (int)W, (int)stats_border);
     count_launch();
     return finish_launch();
 }

@@ -85,23 +85,73 @@ def _as_cuda_u8(img):
     return t.contiguous(), host
 
 
-def gen_flow_warp(img, params, want_flow=True, want_mask=True):
+def gen_flow_warp(img, params, want_flow=True, want_mask=True, want_flow2=False, stats_border=0):
     """Kernel-level entry: ``img`` CUDA uint8 [B,H,W], ``params`` list of B 8-tuples
     (:func:`fold_line_params`).  -> (deformed [B,H,W] u8, flow [B,H,W,2] f32 | None,
-    mask [B,H,W] u8 | None, stats [B,2] int64 CUDA: zero count, pixel sum)."""
+    mask [B,H,W] u8 | None, stats [B,2] int64 CUDA: zero count, pixel sum) and, with
+    ``want_flow2``, the data providers' second flow as a fifth element."""
     B, H, W = img.shape
     dev = img.device
     p = torch.tensor(params, dtype=torch.float64).reshape(B, 8).to(dev)
     out = torch.empty_like(img)
     flow = torch.empty((B, H, W, 2), dtype=torch.float32, device=dev) if want_flow else None
+    flow2 = torch.empty((B, H, W, 2), dtype=torch.float32, device=dev) if want_flow2 else None
     mask = torch.empty_like(img) if want_mask else None
     stats = torch.empty((B, 2), dtype=torch.int64, device=dev)
     code = _lib.load().sstem_sff_degrade(
         img.data_ptr(), p.data_ptr(), out.data_ptr(), flow.data_ptr() if want_flow else None,
-        mask.data_ptr() if want_mask else None, stats.data_ptr(), B, H, W, torch.cuda.current_stream(dev).cuda_stream)
+        flow2.data_ptr() if want_flow2 else None, mask.data_ptr() if want_mask else None, stats.data_ptr(),
+        B, H, W, stats_border, torch.cuda.current_stream(dev).cuda_stream)
     if code:
         _lib.check(code, "sstem_sff_degrade")
-    return out, flow, mask, stats
+    return (out, flow, mask, stats, flow2) if want_flow2 else (out, flow, mask, stats)
+
+
+def gen_flow(height, width, k, b, line_width=5, fold_width=10, dis_k=0.1, two_flows=False):
+    """Drop-in for ``gen_flow`` (simu_sff/flow_synthesis.py:27-83; with ``two_flows`` the data providers'
+    variant, sff_scripts_unfolding/utils/flow_synthesis.py:27-61, which also returns ``flow2``), evaluated by
+    the kernel: -> (flow float32 [H,W,2], [flow2,] mask float64 [H,W]) as numpy arrays, bit-equal."""
+    if not torch.cuda.is_available():
+        raise _lib.SstemError("sstem_restoration_b200 sff_sim: no CUDA device; there is no CPU fallback")
+    img = torch.zeros((1, height, width), dtype=torch.uint8, device=torch.device("cuda", torch.cuda.current_device()))
+    res = gen_flow_warp(img, [fold_line_params(k, b, line_width, fold_width, dis_k)], want_flow2=two_flows)
+    flow, mask = res[1][0].cpu().numpy(), res[2][0].cpu().numpy().astype(np.float64)
+    return (flow, res[4][0].cpu().numpy(), mask) if two_flows else (flow, mask)
+
+
+def provider_degradation(img, crop_size, offset, rng=_random, line_width_max=50):
+    """``Provider.degradation`` of the training data providers on the GPU
+    (sff_scripts_unfolding/data/data_provider.py:180-245; the fusion provider is the same with
+    ``line_width_max=20``, sff_scripts_fusion/data/data_provider.py:188): fold line through two random
+    border points, both flows, warp, mask, centre crop by ``offset``, accepted once the crop holds >= 100
+    zero pixels.  -> (deformed uint8 [crop-2*offset]^2, flow2 float32 [.., .., 2])."""
+    t, host = _as_cuda_u8(img)
+    if t.dim() != 2:
+        raise ValueError("provider_degradation: one [H,W] image")
+    t = t[None]
+    while True:
+        height = width = crop_size
+        line_width = rng.randint(5, line_width_max)
+        fold_width = rng.randint(line_width + 1, 80)
+        k1 = rng.randint(1, 4)
+        k2 = rng.randint(1, 4)
+        while k1 == k2:
+            k2 = rng.randint(1, 4)
+        pts = []
+        for side in (k1, k2):                             # data_provider.py:195-219: one draw per point, no offset rule
+            x = rng.randint(1, (width if side in (1, 3) else height) - 1)
+            pts.append({1: [0, x], 2: [x, width], 3: [height, x], 4: [x, 0]}[side])
+        dis_k = rng.uniform(0.00001, 0.1)
+        k, b = gen_line(pts[0], pts[1])
+        out, _, _, stats, flow2 = gen_flow_warp(t, [fold_line_params(k, b, line_width, fold_width, dis_k)],
+                                                want_flow=False, want_mask=False, want_flow2=True, stats_border=offset)
+        if int(stats[0, 0].item()) >= 100:
+            break
+    sl = slice(offset, -offset) if offset else slice(None)
+    deformed, flow2 = out[0][sl, sl], flow2[0][sl, sl]
+    if host:
+        return deformed.cpu().numpy(), flow2.cpu().numpy()
+    return deformed.contiguous(), flow2.contiguous()
 
 
 def degradation(img, crop_size, offset=50, rng=_random, return_stats=False):

@@ -66,8 +66,9 @@ def gen_line(p1, p2):
     return k, p1[0] - k * p1[1]
 
 
-def gen_flow(height, width, k, b, line_width=5, fold_width=10, dis_k=0.1):
-    """flow_synthesis.py:27-83 -> (flow float32 [H,W,2], mask float64 [H,W]).
+def gen_flow(height, width, k, b, line_width=5, fold_width=10, dis_k=0.1, two_flows=False):
+    """flow_synthesis.py:27-83 -> (flow float32 [H,W,2], mask float64 [H,W]); with ``two_flows`` the data
+    providers' variant (sff_scripts_unfolding/utils/flow_synthesis.py:27-61) -> (flow, flow2, mask).
 
     Signed distance to the fold line; inside the line (|d| <= line_width) the
     displacement equals the distance, outside it decays linearly from
@@ -89,19 +90,29 @@ def gen_flow(height, width, k, b, line_width=5, fold_width=10, dis_k=0.1):
     off = (fold_width - line_width) - slope * line_width
     mag = slope * ad + off
     mag[mag < 0] = 0
+    if two_flows:                                          # unfolding flow_synthesis.py:48-49,58,62
+        beyond = np.ones_like(d)
+        beyond[ad < fold_width] = 0
+        d2 = (mag * beyond + ad * (1 - beyond)) * (-sign)
     mag = mag * outside + ad * (1 - outside)
     d = mag * sign
     k_t = 1 / _MINA if k == 0 else 1 / k
     ang = math.atan(k_t)
     s, c = math.sin(ang), math.cos(ang)
-    flow = np.zeros((height, width, 2), dtype=np.float32)
-    if k > 0:
-        flow[:, :, 0] = d * c
-        flow[:, :, 1] = -(d * s)
-    else:
-        flow[:, :, 0] = -(d * c)
-        flow[:, :, 1] = d * s
-    return flow, mask
+
+    def project(dd):
+        fl = np.zeros((height, width, 2), dtype=np.float32)
+        if k > 0:
+            fl[:, :, 0] = dd * c
+            fl[:, :, 1] = -(dd * s)
+        else:
+            fl[:, :, 0] = -(dd * c)
+            fl[:, :, 1] = dd * s
+        return fl
+
+    if two_flows:
+        return project(d), project(d2), mask
+    return project(d), mask
 
 
 def random_fold_flow(height, width, seed=555):

@@ -72,6 +72,12 @@ def simu_sff_cases():
     return {"p256_seed555": (256, 3, 555), "p256_seed1": (256, 4, 1), "p300_seed77": (300, 5, 77)}
 
 
+def provider_degradation_cases():
+    """name -> (crop size, offset, section index, random.seed, provider) for Provider.degradation + noise
+    of the training data providers (det_size = crop - 2*offset = 256 as in data_provider.py:94-95)."""
+    return {"unfolding_c320_seed3": (320, 32, 6, 3, "unfolding"), "fusion_c288_seed11": (288, 16, 7, 11, "fusion")}
+
+
 def sepconv_cases():
     """name -> dict(B, C, H, W, seed, scale): seeded sepconv inputs (K = 51)."""
     return {

@@ -104,6 +104,31 @@ def main():
         out[name + "_flow_sha256"] = np.frombuffer(hashlib.sha256(np.ascontiguousarray(flow).tobytes()).digest(), np.uint8)
         out[name + "_mask"] = np.packbits(mask.astype(np.uint8))
         out[name + "_noise"] = ref_sim.noise(deformed.copy(), size)
+    # ---- the training data providers' degradation + noise: the reference's own method source, executed ----
+    # data_provider.py cannot be imported (cv2, h5py, tifffile, torchvision...); the two methods are plain numpy +
+    # random, so their source text is cut out of the file and exec'd unmodified with the reference's gen_line /
+    # gen_flow (utils/flow_synthesis.py, the three-output variant) and image_warp in scope.
+    import textwrap
+    for name, (crop, offset, index, seed, which) in cases.provider_degradation_cases().items():
+        root = os.path.join(REF, "sff_scripts_" + which)
+        fs = _load(os.path.join(root, "utils", "flow_synthesis.py"), "ref_fs_" + which)
+        src = open(os.path.join(root, "data", "data_provider.py")).read()
+        a = src.index("\tdef degradation(self, img):")
+        b = src.index("\t@staticmethod", a)
+        ns = {"np": np, "random": random, "gen_line": fs.gen_line, "gen_flow": fs.gen_flow, "image_warp": ref_np.image_warp}
+        exec(textwrap.dedent(src[a:b].replace("\t", "    ")), ns)
+        me = types.SimpleNamespace(crop_size=[crop, crop], offset=offset, det_size=crop - 2 * offset)
+        img = synth.em_section(crop, crop, index)
+        random.seed(seed)
+        deformed, flow2 = ns["degradation"](me, img)
+        out[name + "_deformed"] = deformed
+        out[name + "_flow2_sha256"] = np.frombuffer(hashlib.sha256(np.ascontiguousarray(flow2).tobytes()).digest(), np.uint8)
+        out[name + "_noise"] = ns["noise"](me, deformed.copy())
+    # the three-output gen_flow on its own (small, kept whole)
+    fs = _load(os.path.join(REF, "sff_scripts_unfolding", "utils", "flow_synthesis.py"), "ref_fs_unfolding2")
+    k, b = fs.gen_line([0, 20], [64, 60])
+    f1, f2, m = fs.gen_flow(64, 80, k, b, 5, 30, 0.05)
+    out["gen_flow3_flow"], out["gen_flow3_flow2"], out["gen_flow3_mask"] = f1, f2, m.astype(np.uint8)
     np.savez_compressed(os.path.join(HERE, "simu_sff_ref.npz"), **out)
     print("simuSFF cases:", {k: v.shape for k, v in out.items() if k.endswith("_noise")})
 

@@ -99,3 +99,34 @@ def test_rejects_non_uint8_and_bad_rank():
         sff_sim.degradation(torch.zeros((256, 256), device="cuda"), 256)
     with pytest.raises(ValueError):
         sff_sim.degradation(torch.zeros((2, 2, 2, 2), dtype=torch.uint8, device="cuda"), 256)
+
+
+@pytest.mark.parametrize("name", list(cases.provider_degradation_cases()))
+def test_provider_degradation_matches_reference_outputs(golden_dir, name):
+    """The data providers' degradation + noise (data_provider.py:180-259) on the GPU vs the reference's
+    own method source run with the same random.seed."""
+    ref = np.load(os.path.join(golden_dir, "simu_sff_ref.npz"))
+    crop, offset, index, seed, which = cases.provider_degradation_cases()[name]
+    rng = random.Random(seed)
+    img = torch.from_numpy(synth.em_section(crop, crop, index)).cuda()
+    deformed, flow2 = sff_sim.provider_degradation(img, crop, offset, rng=rng, line_width_max=50 if which == "unfolding" else 20)
+    out = sff_sim.noise(deformed, crop - 2 * offset, rng=rng)
+    assert np.array_equal(deformed.cpu().numpy(), ref[name + "_deformed"])
+    assert hashlib.sha256(np.ascontiguousarray(flow2.cpu().numpy()).tobytes()).digest() == ref[name + "_flow2_sha256"].tobytes()
+    assert np.array_equal(out.cpu().numpy(), ref[name + "_noise"])
+
+
+def test_gen_flow_drop_in_bit_exact(golden_dir):
+    ref = np.load(os.path.join(golden_dir, "gen_flow_ref.npz"))
+    for name, (h, w, p1, p2, lw, fw, dk) in cases.gen_flow_cases().items():
+        k, b = sff_sim.gen_line(p1, p2)
+        flow, mask = sff_sim.gen_flow(h, w, k, b, lw, fw, dk)
+        assert flow.dtype == np.float32 and mask.dtype == np.float64
+        assert np.array_equal(flow.view(np.uint32), ref[name + "_flow"].view(np.uint32)), name
+        assert np.array_equal(mask.astype(np.uint8), ref[name + "_mask"]), name
+    ref3 = np.load(os.path.join(golden_dir, "simu_sff_ref.npz"))
+    k, b = sff_sim.gen_line([0, 20], [64, 60])
+    f1, f2, m = sff_sim.gen_flow(64, 80, k, b, 5, 30, 0.05, two_flows=True)
+    assert np.array_equal(f1.view(np.uint32), ref3["gen_flow3_flow"].view(np.uint32))
+    assert np.array_equal(f2.view(np.uint32), ref3["gen_flow3_flow2"].view(np.uint32))
+    assert np.array_equal(m.astype(np.uint8), ref3["gen_flow3_mask"])

@@ -166,3 +166,30 @@ def test_simu_sff_restatement_matches_reference_bitwise(golden_dir, name):
     assert hashlib.sha256(np.ascontiguousarray(flow).tobytes()).digest() == ref[name + "_flow_sha256"].tobytes()
     assert np.array_equal(np.packbits(mask.astype(np.uint8)), ref[name + "_mask"])
     assert np.array_equal(oracle.sff_noise_restated(deformed, size, rng), ref[name + "_noise"])
+
+
+@pytest.mark.parametrize("name", list(cases.provider_degradation_cases()))
+def test_provider_degradation_restatement_matches_reference_bitwise(golden_dir, name):
+    """oracle.provider_degradation_restated + sff_noise_restated against the data providers' own
+    `degradation` / `noise` method source executed by tests/golden/make_golden.py."""
+    import hashlib
+    import random
+    from sstem_restoration_b200 import synth
+    ref = np.load(os.path.join(golden_dir, "simu_sff_ref.npz"))
+    crop, offset, index, seed, which = cases.provider_degradation_cases()[name]
+    rng = random.Random(seed)
+    deformed, flow2 = oracle.provider_degradation_restated(synth.em_section(crop, crop, index), crop, offset, rng,
+                                                           line_width_max=50 if which == "unfolding" else 20)
+    assert np.array_equal(deformed, ref[name + "_deformed"])
+    assert hashlib.sha256(np.ascontiguousarray(flow2).tobytes()).digest() == ref[name + "_flow2_sha256"].tobytes()
+    assert np.array_equal(oracle.sff_noise_restated(deformed, crop - 2 * offset, rng), ref[name + "_noise"])
+
+
+def test_three_output_gen_flow_restatement_matches_reference_bitwise(golden_dir):
+    from sstem_restoration_b200 import synth
+    ref = np.load(os.path.join(golden_dir, "simu_sff_ref.npz"))
+    k, b = synth.gen_line([0, 20], [64, 60])
+    f1, f2, m = synth.gen_flow(64, 80, k, b, 5, 30, 0.05, two_flows=True)
+    assert np.array_equal(f1.view(np.uint32), ref["gen_flow3_flow"].view(np.uint32))
+    assert np.array_equal(f2.view(np.uint32), ref["gen_flow3_flow2"].view(np.uint32))
+    assert np.array_equal(m.astype(np.uint8), ref["gen_flow3_mask"])
