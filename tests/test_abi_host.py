@@ -140,3 +140,57 @@ def test_synth_inputs_are_deterministic_and_shaped():
     assert t.shape == (2, 51, 8, 8) and np.allclose(t.sum(1), 1, atol=1e-5)
     f, m = synth.random_fold_flow(128, 128)
     assert f.shape == (128, 128, 2) and f.dtype == np.float32 and set(np.unique(m)) <= {0.0, 1.0}
+
+
+def test_argument_errors_of_the_section_8f_entry_points(built_lib):
+    """Fused tail, SFF simulation and stack I/O: argument checks run before any CUDA call."""
+    from sstem_restoration_b200 import _lib
+    lib = _lib.load()
+    buf = ctypes.create_string_buffer(256)
+    p = ctypes.addressof(buf)
+    taps = [p] * 4
+    assert lib.sstem_interp_tail_forward(None, p, 48, *taps, p, 1, 3, 4, 4, 51, 0, None) == -1
+    assert lib.sstem_interp_tail_forward(p, p, 48, *taps, p, 1, 3, 4, 4, 49, 0, None) == -2       # 51 taps only
+    assert lib.sstem_interp_tail_forward(p, p, 47, *taps, p, 1, 3, 4, 4, 51, 0, None) == -2       # batch stride < C*H*W
+    assert lib.sstem_interp_tail_forward(p, p, 48, *taps, p, 1, 3, 4, 4, 51, 1, None) == -5       # STRICT_ORDER not offered
+    assert lib.sstem_interp_tail_forward(p, p + 2, 48, *taps, p, 1, 3, 4, 4, 51, 0, None) == -3
+    assert lib.sstem_interp_tail_backward(p, p, p, 48, *taps, None, None, None, None, 1, 3, 4, 4, 51, 0, None) == -1
+    assert lib.sstem_sff_degrade(None, p, p, None, None, None, p, 1, 4, 4, 0, None) == -1
+    assert lib.sstem_sff_degrade(p, p, p, None, None, None, p, 1, 4, 4, 2, None) == -2           # border swallows the image
+    assert lib.sstem_sff_degrade(p, p + 4, p, None, None, None, p, 1, 4, 4, 0, None) == -3       # params not 8-byte aligned
+    assert lib.sstem_sff_contrast(p, p, p, 1, 4, 4, 0, 4, None) == -2
+    assert lib.sstem_sections_to_input(p, None, p, 1, 4, 4, 0, None) == -1
+    assert lib.sstem_sections_to_input(p, p, p, 1, 4, 4, -1, None) == -2
+    assert lib.sstem_prediction_to_u8(p, None, 1, 4, 4, 0, None) == -1
+    assert lib.sstem_prediction_to_u8(p + 1, p, 1, 4, 4, 0, None) == -3
+
+
+def test_section_8f_host_mirrors_refuse_to_run_without_cuda(built_lib):
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    import sstem_restoration_b200 as pkg
+    with pytest.raises(NotImplementedError):            # as SeparableConvolution.py:47-48
+        pkg.interpolation_tail(*(torch.zeros((1, 3, 4, 4)) for _ in range(2)), *(torch.zeros((1, 51, 4, 4)) for _ in range(4)))
+    with pytest.raises(pkg.SstemError):
+        pkg.sff_sim.degradation(np.zeros((256, 256), np.uint8), 256)
+    with pytest.raises(pkg.SstemError):
+        pkg.sections_to_input(np.zeros((4, 4), np.uint8), np.zeros((4, 4), np.uint8))
+    with pytest.raises(pkg.SstemError):
+        pkg.sff_sim.gen_flow(8, 8, 1.0, 0.0)
+
+
+def test_host_side_fold_line_logic_matches_oracle():
+    """get_two_points / gen_line / fold_line_params draw and derive exactly what the oracle restatement does."""
+    import math
+    import random
+    import oracle
+    from sstem_restoration_b200 import sff_sim, synth
+    for seed in range(5):
+        a, b = random.Random(seed), random.Random(seed)
+        assert sff_sim.get_two_points(256, 256, 50, 256, a) == oracle.sff_get_two_points(256, 256, 50, 256, b)
+        assert a.random() == b.random()                  # same number of draws consumed
+    k, bb = sff_sim.gen_line([0, 70], [256, 190])
+    assert (k, bb) == synth.gen_line([0, 70], [256, 190])
+    prm = sff_sim.fold_line_params(k, bb, 7, 33, 0.02)
+    assert prm[2] == math.sqrt(k ** 2 + 1) and prm[6] == math.sin(math.atan(1 / k)) and prm[7] == math.cos(math.atan(1 / k))
+    assert sff_sim.fold_line_params(0, 3.0, 7, 33, 0.02)[6] == math.sin(math.atan(1 / 0.000000001))
