@@ -96,6 +96,59 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def cpu_simu_sff_sample(calls: int = 10):
+    """cpu_baseline leg for BASELINE config 1: the reference's numpy SimuSFF (degradation + noise) restated in
+    oracle/ (bit-equal to simu_sff/simuSFF.py:96-144), one host core, 256x256 sections.  -> seconds per call."""
+    import random
+    import oracle
+    from sstem_restoration_b200 import synth
+    img = synth.em_section(256, 256, 1)
+    rng = random.Random(5)
+    t0 = time.perf_counter()
+    for _ in range(calls):
+        d, _, _ = oracle.sff_degradation_restated(img, 256, rng)
+        oracle.sff_noise_restated(d, 256, rng)
+    return (time.perf_counter() - t0) / calls
+
+
+def run_simu_sff(pkg, dev):
+    """BASELINE config 1 on the GPU: sff_sim.simu_sff on a 256x256 section (host accept loop included), and the
+    degrade kernel alone at the config-5 section size."""
+    import random
+    import torch
+    from sstem_restoration_b200 import sff_sim, synth
+    img = torch.from_numpy(synth.em_section(256, 256, 1)).to(dev)
+    rng = random.Random(5)
+    for _ in range(3):
+        sff_sim.simu_sff(img, 256, rng=rng)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    n = 20
+    for _ in range(n):
+        sff_sim.simu_sff(img, 256, rng=rng)
+    torch.cuda.synchronize()
+    call_ms = (time.perf_counter() - t0) / n * 1e3
+    big = torch.from_numpy(synth.em_section(512, 512, 2)).to(dev).repeat(8, 8)[None].contiguous()
+    k, b = synth.gen_line([0, 1400], [4096, 2700])
+    prm = [sff_sim.fold_line_params(k, b, 12, 60, 0.05)]
+    for _ in range(3):
+        sff_sim.gen_flow_warp(big, prm, want_flow=False, want_mask=False)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        sff_sim.gen_flow_warp(big, prm, want_flow=False, want_mask=False)
+    e1.record()
+    torch.cuda.synchronize()
+    kms = e0.elapsed_time(e1) / 10
+    cpu_s = cpu_simu_sff_sample()
+    return {"config": "c1: SimuSFF (degradation + noise) on a uint8 256x256 EM-like section; bit-equal to the reference's numpy run",
+            "gpu_ms_per_call_256": round(call_ms, 4), "gpu_mpix_per_s_256": round(256 * 256 / call_ms / 1e3, 1),
+            "cpu_numpy_ms_per_call_256": round(cpu_s * 1e3, 3), "cpu_mpix_per_s_256": round(256 * 256 / cpu_s / 1e6, 2), "cpu_cores": 1,
+            "degrade_kernel_4096_ms": round(kms, 4), "degrade_kernel_4096_gpix_per_s": round(4096 * 4096 / kms / 1e6, 1),
+            "note": "the 256x256 call is launch- and sync-bound (one 8-byte read per accept attempt); NOT the headline"}
+
+
 def _traffic():
     """DRAM bytes per launch from the committed `ncu --set full` captures (profiles/traffic_r1.json)."""
     path = os.path.join(ROOT, "profiles", "traffic_r1.json")
@@ -321,6 +374,7 @@ def run_gpu_arm(args):
     # ---- warp (config 4) on the same device, reported beside the headline -------------------
     warp = run_warp(args, pkg, dev) if not args.no_warp else None
     tail = run_tail(pkg, dev, B, H, W) if (not args.no_warp and rank == 0) else None
+    simu = run_simu_sff(pkg, dev) if (not args.no_warp and rank == 0) else None
 
     if rank != 0:
         if world > 1:
@@ -371,7 +425,7 @@ def run_gpu_arm(args):
         "cpu_baseline": {"value": round(cpu_val, 4), "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": cpu_sample},
         "e2e": e2e, "gpu_launches": int(lsum.item()), "clocks": clocks,
         "extra": {"fwd_mpix_per_s": round(px_call / (fwd_ms * 1e-3) / 1e6, 1), "bwd_taps_mpix_per_s": round(px_call / (bwd_ms * 1e-3) / 1e6, 1),
-                  "warp": warp, "gray_x3_shortcut": gray, "fused_interp_tail": tail, "ms_per_step_by_rank": per_rank},
+                  "warp": warp, "gray_x3_shortcut": gray, "fused_interp_tail": tail, "simu_sff_c1": simu, "ms_per_step_by_rank": per_rank},
     }
     print(json.dumps(line), flush=True)
     if world > 1:
