@@ -96,6 +96,37 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def cpu_warp_sample():
+    """cpu_baseline leg for the warps: the numpy `image_warp` (simu_sff/image_warp.py, restated bit-equal in
+    oracle/) on a uint8 256x256 section and a float 1024x1024x3 one, and the numpy restatement of
+    SpatialTransformation.forward on [1,3,1024,1024]; one host core (numpy fancy indexing is single-threaded)."""
+    import numpy as np
+    import oracle
+    from sstem_restoration_b200 import synth
+    res = {"cores": 1}
+    for name, n, c in (("image_warp_u8_256", 256, 0), ("image_warp_f32_1024x3", 1024, 3)):
+        sec = synth.em_section(n, n, 3)
+        im = sec if c == 0 else np.repeat(sec[..., None].astype(np.float32), c, axis=2)
+        flow, _ = synth.random_fold_flow(n, n, 555)
+        oracle.image_warp_restated(im, flow)
+        t0 = time.perf_counter()
+        reps = 5 if n == 256 else 2
+        for _ in range(reps):
+            oracle.image_warp_restated(im, flow)
+        dt = (time.perf_counter() - t0) / reps
+        res[name + "_mpix_per_s"] = round(n * n / dt / 1e6, 2)
+    n = 1024
+    moving = np.repeat((synth.em_section(n, n, 4).astype(np.float32) / 255.0)[None, None], 3, 1)
+    flow, _ = synth.random_fold_flow(n, n, 555)
+    oracle.warp_torch_restated(moving, flow[None])
+    t0 = time.perf_counter()
+    oracle.warp_torch_restated(moving, flow[None])
+    dt = time.perf_counter() - t0
+    res["spatial_transformation_1024x3_mpix_per_s"] = round(n * n / dt / 1e6, 2)
+    res["spatial_transformation_1024x3_gb_per_s"] = round(32 * n * n / dt / 1e9, 3)
+    return res
+
+
 def cpu_simu_sff_sample(calls: int = 10):
     """cpu_baseline leg for BASELINE config 1: the reference's numpy SimuSFF (degradation + noise) restated in
     oracle/ (bit-equal to simu_sff/simuSFF.py:96-144), one host core, 256x256 sections.  -> seconds per call."""
@@ -414,6 +445,8 @@ def run_gpu_arm(args):
                            "no fp32 row")
 
     cpu_val, cpu_dt, cpu_sample = cpu_sepconv_sample(steps=3, warmup=1)
+    if warp:
+        warp["cpu_baseline"] = cpu_warp_sample()
     line = {
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
