@@ -102,3 +102,16 @@ def sepconv_inputs(B, C, H, W, seed, kind, K=51):
         inp = r.standard_normal((B, C, H + K - 1, W + K - 1)).astype(np.float32)
     g = r.standard_normal((B, C, H, W)).astype(np.float32)
     return inp, v, h, g
+
+
+def kpn_taps_case():
+    """BASELINE config 2: random-init KPN (torch.manual_seed) on two synthetic 256x256 sections; crop of the taps kept."""
+    return dict(size=256, section_a=11, section_b=12, torch_seed=0, crop_y=40, crop_x=200, crop=32)
+
+
+def kpn_frames(p):
+    """[1,6,H,W] float32 network input exactly as sff_scripts_interp/inference.py:69-77 builds it (gray x3, /255)."""
+    from sstem_restoration_b200 import synth
+    a = synth.em_section(p["size"], p["size"], p["section_a"]).astype(np.float32) / 255.0
+    b = synth.em_section(p["size"], p["size"], p["section_b"]).astype(np.float32) / 255.0
+    return np.concatenate([np.repeat(a[None], 3, 0), np.repeat(b[None], 3, 0)], 0)[None].astype(np.float32)

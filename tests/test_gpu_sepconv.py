@@ -348,3 +348,28 @@ def test_operator_runs_on_a_non_current_device_stream_pair():
     assert torch.cuda.current_device() == 0
     out = pkg.SeparableConvolution.apply(*t)
     assert out.device.index == 1 and torch.equal(out.cpu(), ref)
+
+
+# ---------------------------------------------------------------- BASELINE config 2: taps from the reference's own KPN
+def _kpn_crop_inputs(golden_dir):
+    p = cases.kpn_taps_case()
+    taps = np.load(os.path.join(golden_dir, "kpn_taps_ref.npz"))
+    x = cases.kpn_frames(p)
+    y0, x0, n = p["crop_y"], p["crop_x"], p["crop"]
+    pad = lambda f: np.pad(f, ((0, 0), (0, 0), (25, 25), (25, 25)), mode="edge")[:, :, y0:y0 + n + 50, x0:x0 + n + 50]
+    return np.ascontiguousarray(pad(x[:, :3])), np.ascontiguousarray(pad(x[:, 3:6])), taps
+
+
+def test_c2_taps_from_reference_kpn(golden_dir):
+    """Raw 51-tap kernels predicted by the reference's random-init IFNet (tests/golden/make_kpn_taps_golden.py; |taps| up
+    to ~6, |out| ~ 1e1): protocol P2 for the forward of both frames and for the tap gradients."""
+    i1, i2, taps = _kpn_crop_inputs(golden_dir)
+    g = np.random.default_rng(5).standard_normal((1, 3, 32, 32)).astype(np.float32)
+    for inp, v, h in ((i2, taps["k2v"], taps["k2h"]), (i1, taps["k1v"], taps["k1h"])):
+        out, gi, gv, gh = _bwd(*_cuda(inp, v, h, g), need_input=False)
+        _check_p(out.cpu().numpy(), oracle.sepconv_forward_reforder(inp, v, h), oracle.sepconv_forward_f64(inp, v, h), "kpn fwd")
+        gv64, gh64 = oracle.sepconv_grad_taps_f64(g, inp, v, h)
+        _check_p(gv.cpu().numpy(), oracle.sepconv_grad_vertical_reforder(g, inp, h), gv64, "kpn gv")
+        _check_p(gh.cpu().numpy(), oracle.sepconv_grad_horizontal_reforder(g, inp, v), gh64, "kpn gh")
+        strict = _fwd(*_cuda(inp, v, h), strict=True).cpu().numpy()
+        assert np.array_equal(strict.view(np.uint32), oracle.sepconv_forward_reforder(inp, v, h).view(np.uint32))

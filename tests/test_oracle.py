@@ -193,3 +193,32 @@ def test_three_output_gen_flow_restatement_matches_reference_bitwise(golden_dir)
     assert np.array_equal(f1.view(np.uint32), ref["gen_flow3_flow"].view(np.uint32))
     assert np.array_equal(f2.view(np.uint32), ref["gen_flow3_flow2"].view(np.uint32))
     assert np.array_equal(m.astype(np.uint8), ref["gen_flow3_mask"])
+
+
+# ------------------------------------------------------------------ config 2: taps from the reference's KPN
+def test_kpn_taps_fixture_and_compat_import_path(golden_dir):
+    """The committed taps were predicted by the reference's own IFNet imported through compat/ (the zero-edit drop-in
+    path); here: the drop-in resolves at the reference's import path, and on those raw taps the reference summation
+    order is within its usual distance of fp64 (what protocol P2 measures the kernels against)."""
+    import importlib
+    import sys
+    compat = os.path.join(os.path.dirname(golden_dir), "..", "sstem_restoration_b200", "compat")
+    sys.path.insert(0, os.path.abspath(compat))
+    try:
+        mod = importlib.import_module("libs.sepconv.SeparableConvolution")     # model_interp.py:5
+    finally:
+        sys.path.pop(0)
+    import sstem_restoration_b200 as pkg
+    assert mod.SeparableConvolution is pkg.SeparableConvolution
+    with pytest.raises(NotImplementedError):                                   # SeparableConvolution.py:47-48
+        mod.SeparableConvolution.apply(torch.zeros(1, 3, 51, 51), torch.zeros(1, 51, 1, 1), torch.zeros(1, 51, 1, 1))
+    p = cases.kpn_taps_case()
+    taps = np.load(os.path.join(golden_dir, "kpn_taps_ref.npz"))
+    assert taps["k1v"].shape == (1, 51, p["crop"], p["crop"]) and float(np.abs(taps["k2h"]).max()) > 1.0
+    x = cases.kpn_frames(p)
+    y0, x0, n = p["crop_y"], p["crop_x"], p["crop"]
+    inp = np.ascontiguousarray(oracle._replicate_pad(x[:, 3:6])[:, :, y0:y0 + n + 50, x0:x0 + n + 50])
+    ref32 = oracle.sepconv_forward_reforder(inp, taps["k2v"], taps["k2h"])
+    ref64 = oracle.sepconv_forward_f64(inp, taps["k2v"], taps["k2h"])
+    scale = max(1.0, float(np.abs(ref64).max()))
+    assert float(np.abs(ref32 - ref64).max()) <= 1e-5 * scale
