@@ -31,6 +31,12 @@ def _worker(rank, world, port, n_units, q):
         ok = ok and one.shape == (n_units, 2, 3) and all(bool((one[k] == k).all()) for k in range(n_units))
     else:
         ok = ok and one is None
+    # uint8 sections (what tools/stack_restore.py gathers) keep their dtype and order
+    u8 = shard.gather_sections(local.to(torch.uint8), n_units, dst=0)
+    if rank == 0:
+        ok = ok and u8.dtype == torch.uint8 and u8.shape == (n_units, 2, 3) and all(bool((u8[k] == k).all()) for k in range(n_units))
+    else:
+        ok = ok and u8 is None
     # timing reduction used by bench.py: max over ranks
     t = torch.tensor([float(rank + 1)])
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
