@@ -119,6 +119,94 @@ def gen_flow(height, width, k, b, line_width=5, fold_width=10, dis_k=0.1, two_fl
     return (flow, res[4][0].cpu().numpy(), mask) if two_flows else (flow, mask)
 
 
+def _draw_provider_line(crop_size, rng, line_width_max):
+    """One attempt's draws of Provider.degradation (data_provider.py:185-222), in the reference's order."""
+    height = width = crop_size
+    line_width = rng.randint(5, line_width_max)
+    fold_width = rng.randint(line_width + 1, 80)
+    k1 = rng.randint(1, 4)
+    k2 = rng.randint(1, 4)
+    while k1 == k2:
+        k2 = rng.randint(1, 4)
+    pts = []
+    for side in (k1, k2):                                 # data_provider.py:195-219: one draw per point, no offset rule
+        x = rng.randint(1, (width if side in (1, 3) else height) - 1)
+        pts.append({1: [0, x], 2: [x, width], 3: [height, x], 4: [x, 0]}[side])
+    dis_k = rng.uniform(0.00001, 0.1)
+    k, b = gen_line(pts[0], pts[1])
+    return fold_line_params(k, b, line_width, fold_width, dis_k)
+
+
+def _draw_noise_box(det_size, rng):
+    """The draws of `noise` (simuSFF.py:137-141 / data_provider.py:249-254) -> the 8 scalars of sstem_sff_contrast."""
+    ran = rng.uniform(0.4, 1.0)
+    ran_w = rng.randint(50, 200)
+    ran_h = rng.randint(50, 200)
+    px = rng.randint(0, det_size - ran_h)
+    py = rng.randint(0, det_size - ran_w)
+    return [ran, px, py, ran_h, ran_w, 0, 0, 0]
+
+
+def _launch_degrade_batch(imgs, params, offset):
+    """imgs [n,crop,crop] CUDA u8 -> (deformed centre crops [n,det,det] u8, flow2 crops, stats [n,2], zero counts list)."""
+    out, _, _, stats, flow2 = gen_flow_warp(imgs, params, want_flow=False, want_mask=False, want_flow2=True, stats_border=offset)
+    sl = slice(offset, -offset) if offset else slice(None)
+    return out[:, sl, sl].contiguous(), flow2[:, sl, sl].contiguous(), stats, stats[:, 0].tolist()
+
+
+def _launch_contrast_batch(imgs, stats, boxes):
+    """In place on imgs [n,det,det] CUDA u8."""
+    n, H, W = imgs.shape
+    p = torch.tensor(boxes, dtype=torch.float64).reshape(n, 8).to(imgs.device)
+    code = _lib.load().sstem_sff_contrast(imgs.data_ptr(), stats.contiguous().data_ptr(), p.data_ptr(), n, H, W,
+                                          max(int(b[3]) for b in boxes), max(int(b[4]) for b in boxes),
+                                          torch.cuda.current_stream(imgs.device).cuda_stream)
+    if code:
+        _lib.check(code, "sstem_sff_contrast")
+    return imgs
+
+
+def provider_batch(imgs, crop_size, offset, rng=_random, line_width_max=50, with_noise=True):
+    """A whole training batch through ``Provider.degradation`` (+ ``Provider.noise``) of the data providers
+    (data_provider.py:180-259) with ONE degrade launch, one contrast launch and one 8*B-byte read in the common case,
+    yet the same ``random`` draws -- hence bit-identical outputs -- as B sequential per-sample calls: the batch is
+    drawn optimistically (every sample accepted at its first attempt); if sample i is rejected, the samples before it
+    are kept, the generator is rewound to sample i's state with its failed attempt consumed, and the rest is redone.
+    ``imgs``: CUDA uint8 [B, crop_size, crop_size].  -> (sff uint8 [B,det,det], flow2 float32 [B,det,det,2]),
+    det = crop_size - 2*offset."""
+    t, host = _as_cuda_u8(imgs)
+    if t.dim() != 3:
+        raise ValueError("provider_batch: images as [B,H,W]")
+    B = t.shape[0]
+    det = crop_size - 2 * offset
+    sff, flow2 = [], []
+    start = 0
+    while start < B:
+        states, lines, boxes = [], [], []
+        for _ in range(start, B):
+            states.append(rng.getstate())
+            lines.append(_draw_provider_line(crop_size, rng, line_width_max))
+            if with_noise:
+                boxes.append(_draw_noise_box(det, rng))
+        out, fl2, stats, zeros = _launch_degrade_batch(t[start:], lines, offset)
+        bad = next((i for i, z in enumerate(zeros) if z < 100), None)     # data_provider.py:236-241
+        n_ok = len(zeros) if bad is None else bad
+        if n_ok:
+            good = out[:n_ok]
+            if with_noise:
+                good = _launch_contrast_batch(good.contiguous(), stats[:n_ok], boxes[:n_ok])
+            sff.append(good)
+            flow2.append(fl2[:n_ok])
+        if bad is not None:
+            rng.setstate(states[bad])
+            _draw_provider_line(crop_size, rng, line_width_max)             # the failed attempt's draws stay consumed
+        start += n_ok
+    sff, flow2 = torch.cat(sff, 0), torch.cat(flow2, 0)
+    if host:
+        return sff.cpu().numpy(), flow2.cpu().numpy()
+    return sff, flow2
+
+
 def provider_degradation(img, crop_size, offset, rng=_random, line_width_max=50):
     """``Provider.degradation`` of the training data providers on the GPU
     (sff_scripts_unfolding/data/data_provider.py:180-245; the fusion provider is the same with
@@ -130,20 +218,7 @@ def provider_degradation(img, crop_size, offset, rng=_random, line_width_max=50)
         raise ValueError("provider_degradation: one [H,W] image")
     t = t[None]
     while True:
-        height = width = crop_size
-        line_width = rng.randint(5, line_width_max)
-        fold_width = rng.randint(line_width + 1, 80)
-        k1 = rng.randint(1, 4)
-        k2 = rng.randint(1, 4)
-        while k1 == k2:
-            k2 = rng.randint(1, 4)
-        pts = []
-        for side in (k1, k2):                             # data_provider.py:195-219: one draw per point, no offset rule
-            x = rng.randint(1, (width if side in (1, 3) else height) - 1)
-            pts.append({1: [0, x], 2: [x, width], 3: [height, x], 4: [x, 0]}[side])
-        dis_k = rng.uniform(0.00001, 0.1)
-        k, b = gen_line(pts[0], pts[1])
-        out, _, _, stats, flow2 = gen_flow_warp(t, [fold_line_params(k, b, line_width, fold_width, dis_k)],
+        out, _, _, stats, flow2 = gen_flow_warp(t, [_draw_provider_line(crop_size, rng, line_width_max)],
                                                 want_flow=False, want_mask=False, want_flow2=True, stats_border=offset)
         if int(stats[0, 0].item()) >= 100:
             break
@@ -189,20 +264,11 @@ def noise(img, det_size, rng=_random, stats=None):
     if t.dim() != 2:
         raise ValueError("noise: one [H,W] image")
     t = t.clone()[None]
-    H, W = t.shape[1:]
-    ran = rng.uniform(0.4, 1.0)
-    ran_w = rng.randint(50, 200)
-    ran_h = rng.randint(50, 200)
-    px = rng.randint(0, det_size - ran_h)
-    py = rng.randint(0, det_size - ran_w)
+    box = _draw_noise_box(det_size, rng)
     if stats is None:
         stats = torch.stack([(t == 0).sum(), t.sum(dtype=torch.int64)]).reshape(1, 2)
     stats = stats.to(device=t.device, dtype=torch.int64).contiguous()
-    p = torch.tensor([[ran, px, py, ran_h, ran_w, 0, 0, 0]], dtype=torch.float64).to(t.device)
-    code = _lib.load().sstem_sff_contrast(t.data_ptr(), stats.data_ptr(), p.data_ptr(), 1, H, W, ran_h, ran_w,
-                                          torch.cuda.current_stream(t.device).cuda_stream)
-    if code:
-        _lib.check(code, "sstem_sff_contrast")
+    _launch_contrast_batch(t, stats, [box])
     return t[0].cpu().numpy() if host else t[0]
 
 

@@ -194,3 +194,49 @@ def test_host_side_fold_line_logic_matches_oracle():
     prm = sff_sim.fold_line_params(k, bb, 7, 33, 0.02)
     assert prm[2] == math.sqrt(k ** 2 + 1) and prm[6] == math.sin(math.atan(1 / k)) and prm[7] == math.cos(math.atan(1 / k))
     assert sff_sim.fold_line_params(0, 3.0, 7, 33, 0.02)[6] == math.sin(math.atan(1 / 0.000000001))
+
+
+@pytest.mark.parametrize("seed", [0, 3, 7])
+def test_provider_batch_rewind_logic_matches_sequential_calls(monkeypatch, seed):
+    """provider_batch draws the batch optimistically and rewinds the generator when a sample is rejected; with the
+    kernels replaced by the numpy oracle (no GPU here) its outputs must equal B sequential degradation + noise calls
+    bit for bit.  The seeds are chosen so that several samples need 2-5 attempts (data_provider.py:236-241)."""
+    import random
+    import oracle
+    from sstem_restoration_b200 import sff_sim, synth
+    crop, offset, det, B = 448, 96, 256, 5
+    imgs = np.stack([synth.em_section(crop, crop, 20 + i) for i in range(B)])
+
+    def fake_degrade(t, params, off):
+        outs, f2s, stats = [], [], []
+        for img, p in zip(t.numpy(), params):
+            k, b, _, lw, fw, dk, _, _ = p
+            flow, flow2, mask = synth.gen_flow(crop, crop, k, b, int(lw), int(fw), dk, two_flows=True)
+            d = (oracle.image_warp_restated(img, flow) * mask).astype(np.uint8)[off:-off, off:-off]
+            outs.append(d)
+            f2s.append(flow2[off:-off, off:-off])
+            stats.append([int((d == 0).sum()), int(d.sum(dtype=np.int64))])
+        st = torch.tensor(stats, dtype=torch.int64)
+        return torch.from_numpy(np.stack(outs)), torch.from_numpy(np.stack(f2s)), st, st[:, 0].tolist()
+
+    def fake_contrast(t, stats, boxes):
+        for img, s, (ran, px, py, bh, bw, *_) in zip(t.numpy(), stats.tolist(), boxes):
+            mean = s[1] / float(det * det)
+            zero = img == 0
+            box = img[int(px):int(px) + int(bh), int(py):int(py) + int(bw)]
+            img[int(px):int(px) + int(bh), int(py):int(py) + int(bw)] = ran * (box - mean) + mean
+            img[zero] = 0
+        return t
+
+    monkeypatch.setattr(sff_sim, "_as_cuda_u8", lambda x: (torch.as_tensor(x).contiguous(), False))
+    monkeypatch.setattr(sff_sim, "_launch_degrade_batch", fake_degrade)
+    monkeypatch.setattr(sff_sim, "_launch_contrast_batch", fake_contrast)
+    rng = random.Random(seed)
+    sff, flow2 = sff_sim.provider_batch(torch.from_numpy(imgs), crop, offset, rng=rng)
+    ref = random.Random(seed)
+    for i in range(B):
+        d, f2 = oracle.provider_degradation_restated(imgs[i], crop, offset, ref, 50)
+        want = oracle.sff_noise_restated(d, det, ref)
+        assert np.array_equal(sff[i].numpy(), want), (seed, i)
+        assert np.array_equal(flow2[i].numpy().view(np.uint32), f2.view(np.uint32)), (seed, i)
+    assert rng.random() == ref.random()                   # both generators consumed exactly the same draws

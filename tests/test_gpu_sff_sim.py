@@ -130,3 +130,21 @@ def test_gen_flow_drop_in_bit_exact(golden_dir):
     assert np.array_equal(f1.view(np.uint32), ref3["gen_flow3_flow"].view(np.uint32))
     assert np.array_equal(f2.view(np.uint32), ref3["gen_flow3_flow2"].view(np.uint32))
     assert np.array_equal(m.astype(np.uint8), ref3["gen_flow3_mask"])
+
+
+@pytest.mark.parametrize("seed,with_noise", [(0, True), (7, True), (2, False)])
+def test_provider_batch_equals_sequential_reference(seed, with_noise):
+    """One degrade launch + one contrast launch per pass for the whole batch, same draws and outputs as B sequential
+    Provider.degradation / Provider.noise calls (several samples of these seeds need 2-5 attempts)."""
+    crop, offset, det, B = 448, 96, 256, 5
+    imgs = np.stack([synth.em_section(crop, crop, 20 + i) for i in range(B)])
+    rng = random.Random(seed)
+    sff, flow2 = sff_sim.provider_batch(torch.from_numpy(imgs).cuda(), crop, offset, rng=rng, with_noise=with_noise)
+    assert sff.shape == (B, det, det) and flow2.shape == (B, det, det, 2)
+    ref = random.Random(seed)
+    for i in range(B):
+        d, f2 = oracle.provider_degradation_restated(imgs[i], crop, offset, ref, 50)
+        want = oracle.sff_noise_restated(d, det, ref) if with_noise else d
+        assert np.array_equal(sff[i].cpu().numpy(), want), (seed, i)
+        assert np.array_equal(flow2[i].cpu().numpy().view(np.uint32), f2.view(np.uint32)), (seed, i)
+    assert rng.random() == ref.random()
