@@ -61,6 +61,9 @@ constexpr int VDEPTH = 8;                  // steps of vertical taps in flight p
 #define SSTEM_FWD_NPRE1 4                  // the same for the one- / two-channel kernels and the fused tail (measured:
                                            // gray x3 forward +5 %, tail +0.4 %; 8 is no better)
 #endif
+#ifndef SSTEM_UNROLL2
+#define SSTEM_UNROLL2 1                    // one-channel kernels: steady loop two steps per iteration, v registers ping-pong
+#endif
 #ifndef SSTEM_BWD_NPRE
 #define SSTEM_BWD_NPRE 7                   // taps of the next row preloaded during the current step
 #endif
@@ -388,31 +391,47 @@ sepconv_fwd_k51_kernel(const float* __restrict__ in, const float* __restrict__ v
     float2 vcur[Gm::NP], vnext[Gm::NP];
     vr.read(vcur);
     const float* prow = tile + xl + g;                  // P column of tap slot t is xl + g + G*t
-    auto advance = [&]() {                              // make the next step readable, refill the ring
+    auto advance = [&](float2 (&vdst)[Gm::NP]) {        // make the next step readable, refill the ring
         cp_async_wait<VDEPTH - 3>();
         __syncwarp();
         vr.issue();
-        vr.read(vnext);
+        vr.read(vdst);
     };
     float pre[SSTEM_FWD_NPRE + 1];
 #pragma unroll
     for (int t = 0; t < ((CC >= 3) ? SSTEM_FWD_NPRE : SSTEM_FWD_NPRE1); ++t) pre[t] = prow[G * t];
 #define SSTEM_FWD_EDGE_STEP(S)                                                     \
     if ((S) < R - 1 || ((S) >= K51 && (S) < Gm::ROWS)) {                           \
-        advance();                                                                 \
+        advance(vnext);                                                            \
         fwd_step<CC, G, R, S>(prow, novalid, h2, vcur, acc, pre);                       \
         _Pragma("unroll") for (int pp = 0; pp < Gm::NP; ++pp) vcur[pp] = vnext[pp]; \
         prow += Gm::PITCH;                                                         \
     }
     SSTEM_FWD_EDGE_STEP(0) SSTEM_FWD_EDGE_STEP(1) SSTEM_FWD_EDGE_STEP(2) SSTEM_FWD_EDGE_STEP(3)
     SSTEM_FWD_EDGE_STEP(4) SSTEM_FWD_EDGE_STEP(5) SSTEM_FWD_EDGE_STEP(6)
+    // One channel: two steps per iteration with vcur / vnext swapping roles (no register copies; measured +8 % on the
+    // gray forward, +2-6 % on the tail kernels).  Three channels keep the one-step loop (two-step: 0 % forward, -3 %
+    // on the tap gradients).
+    static_assert((K51 - R + 1) % 2 == 0, "the two-step steady loop needs an even number of steady steps");
+    if constexpr (SSTEM_UNROLL2 && CC == 1) {
 #pragma unroll 1
-    for (int s = R - 1; s < K51; ++s) {                 // steady state: all rows active
-        advance();
-        fwd_step<CC, G, R, -1>(prow, novalid, h2, vcur, acc, pre);
+        for (int s = R - 1; s < K51; s += 2) {          // steady state: all rows active
+            advance(vnext);
+            fwd_step<CC, G, R, -1>(prow, novalid, h2, vcur, acc, pre);
+            prow += Gm::PITCH;
+            advance(vcur);
+            fwd_step<CC, G, R, -1>(prow, novalid, h2, vnext, acc, pre);
+            prow += Gm::PITCH;
+        }
+    } else {
+#pragma unroll 1
+        for (int s = R - 1; s < K51; ++s) {             // steady state: all rows active
+            advance(vnext);
+            fwd_step<CC, G, R, -1>(prow, novalid, h2, vcur, acc, pre);
 #pragma unroll
-        for (int pp = 0; pp < Gm::NP; ++pp) vcur[pp] = vnext[pp];
-        prow += Gm::PITCH;
+            for (int pp = 0; pp < Gm::NP; ++pp) vcur[pp] = vnext[pp];
+            prow += Gm::PITCH;
+        }
     }
     SSTEM_FWD_EDGE_STEP(51) SSTEM_FWD_EDGE_STEP(52) SSTEM_FWD_EDGE_STEP(53) SSTEM_FWD_EDGE_STEP(54)
     SSTEM_FWD_EDGE_STEP(55) SSTEM_FWD_EDGE_STEP(56) SSTEM_FWD_EDGE_STEP(57)
@@ -638,10 +657,10 @@ sepconv_bwd_taps_k51_kernel(const float* __restrict__ gout, const float* __restr
     // gv[fy = s - g][y0 + g][x]: pointer for s = 0, advanced by one plane per step
     float* gv_ptr = WV ? gv + b * K51 * plane + (int64_t)min(y0 + g, H - 1) * W + x - (int64_t)g * plane : nullptr;
     const bool gv_row_ok = col_ok && (y0 + g < H);
-    auto advance = [&]() {
+    auto advance = [&](float2 (&vdst)[NP]) {
         cp_async_wait<VDEPTH - 3>();
         __syncwarp();
-        if (WH) { vr.issue(); vr.read(vnext); } else cp_async_commit();
+        if (WH) { vr.issue(); vr.read(vdst); } else cp_async_commit();
     };
     auto store_gv = [&](int s, float2 (&gvp)[NP]) {
         if (WV) {
@@ -662,7 +681,7 @@ sepconv_bwd_taps_k51_kernel(const float* __restrict__ gout, const float* __restr
         for (int t = 0; t < SSTEM_BWD_NPRE; ++t) pre[c][t] = prow[c * Gm::ROWS * Gm::PITCH + G * t];
 #define SSTEM_BWD_EDGE_STEP(S)                                                        \
     if ((S) < R - 1 || ((S) >= K51 && (S) < Gm::ROWS)) {                              \
-        advance();                                                                    \
+        advance(vnext);                                                               \
         bwd_step<CC, G, R, S, WV, WH>(prow, novalid, g2, h2, vcur, gh2, gvp, pre);    \
         store_gv(S, gvp);                                                             \
         _Pragma("unroll") for (int pp = 0; pp < NP; ++pp) vcur[pp] = vnext[pp];       \
@@ -670,14 +689,29 @@ sepconv_bwd_taps_k51_kernel(const float* __restrict__ gout, const float* __restr
     }
     SSTEM_BWD_EDGE_STEP(0) SSTEM_BWD_EDGE_STEP(1) SSTEM_BWD_EDGE_STEP(2) SSTEM_BWD_EDGE_STEP(3)
     SSTEM_BWD_EDGE_STEP(4) SSTEM_BWD_EDGE_STEP(5) SSTEM_BWD_EDGE_STEP(6)
+    static_assert((K51 - R + 1) % 2 == 0, "the two-step steady loop needs an even number of steady steps");
+    if constexpr (SSTEM_UNROLL2 && CC == 1) {            // see sepconv_fwd_k51_kernel
 #pragma unroll 1
-    for (int s = R - 1; s < K51; ++s) {
-        advance();
-        bwd_step<CC, G, R, -1, WV, WH>(prow, novalid, g2, h2, vcur, gh2, gvp, pre);
-        store_gv(s, gvp);
+        for (int s = R - 1; s < K51; s += 2) {
+            advance(vnext);
+            bwd_step<CC, G, R, -1, WV, WH>(prow, novalid, g2, h2, vcur, gh2, gvp, pre);
+            store_gv(s, gvp);
+            prow += Gm::PITCH;
+            advance(vcur);
+            bwd_step<CC, G, R, -1, WV, WH>(prow, novalid, g2, h2, vnext, gh2, gvp, pre);
+            store_gv(s + 1, gvp);
+            prow += Gm::PITCH;
+        }
+    } else {
+#pragma unroll 1
+        for (int s = R - 1; s < K51; ++s) {
+            advance(vnext);
+            bwd_step<CC, G, R, -1, WV, WH>(prow, novalid, g2, h2, vcur, gh2, gvp, pre);
+            store_gv(s, gvp);
 #pragma unroll
-        for (int pp = 0; pp < NP; ++pp) vcur[pp] = vnext[pp];
-        prow += Gm::PITCH;
+            for (int pp = 0; pp < NP; ++pp) vcur[pp] = vnext[pp];
+            prow += Gm::PITCH;
+        }
     }
     SSTEM_BWD_EDGE_STEP(51) SSTEM_BWD_EDGE_STEP(52) SSTEM_BWD_EDGE_STEP(53) SSTEM_BWD_EDGE_STEP(54)
     SSTEM_BWD_EDGE_STEP(55) SSTEM_BWD_EDGE_STEP(56) SSTEM_BWD_EDGE_STEP(57)
@@ -942,32 +976,44 @@ interp_tail_fwd_k51_kernel(const __grid_constant__ TailFrames fa, int64_t frame_
         float2 vcur[Gm::NP], vnext[Gm::NP];
         vr.read(vcur);
         const float* prow = tile + xl + g;
-        auto advance = [&]() {
+        auto advance = [&](float2 (&vdst)[Gm::NP]) {
             cp_async_wait<VDEPTH - 3>();
             __syncwarp();
             vr.issue();
-            vr.read(vnext);
+            vr.read(vdst);
         };
         float pre[SSTEM_FWD_NPRE + 1];
 #pragma unroll
         for (int t = 0; t < SSTEM_FWD_NPRE1; ++t) pre[t] = prow[G * t];
 #define SSTEM_TAIL_EDGE_STEP(S)                                                    \
     if ((S) < R - 1 || ((S) >= K51 && (S) < Gm::ROWS)) {                           \
-        advance();                                                                 \
+        advance(vnext);                                                            \
         fwd_step<1, G, R, S>(prow, novalid, h2, vcur, acc, pre);                   \
         _Pragma("unroll") for (int pp = 0; pp < Gm::NP; ++pp) vcur[pp] = vnext[pp]; \
         prow += Gm::PITCH;                                                         \
     }
         SSTEM_TAIL_EDGE_STEP(0) SSTEM_TAIL_EDGE_STEP(1) SSTEM_TAIL_EDGE_STEP(2) SSTEM_TAIL_EDGE_STEP(3)
         SSTEM_TAIL_EDGE_STEP(4) SSTEM_TAIL_EDGE_STEP(5) SSTEM_TAIL_EDGE_STEP(6)
+#if SSTEM_UNROLL2
+#pragma unroll 1
+        for (int s = R - 1; s < K51; s += 2) {
+            advance(vnext);
+            fwd_step<1, G, R, -1>(prow, novalid, h2, vcur, acc, pre);
+            prow += Gm::PITCH;
+            advance(vcur);
+            fwd_step<1, G, R, -1>(prow, novalid, h2, vnext, acc, pre);
+            prow += Gm::PITCH;
+        }
+#else
 #pragma unroll 1
         for (int s = R - 1; s < K51; ++s) {
-            advance();
+            advance(vnext);
             fwd_step<1, G, R, -1>(prow, novalid, h2, vcur, acc, pre);
 #pragma unroll
             for (int pp = 0; pp < Gm::NP; ++pp) vcur[pp] = vnext[pp];
             prow += Gm::PITCH;
         }
+#endif
         SSTEM_TAIL_EDGE_STEP(51) SSTEM_TAIL_EDGE_STEP(52) SSTEM_TAIL_EDGE_STEP(53) SSTEM_TAIL_EDGE_STEP(54)
         SSTEM_TAIL_EDGE_STEP(55) SSTEM_TAIL_EDGE_STEP(56) SSTEM_TAIL_EDGE_STEP(57)
 #undef SSTEM_TAIL_EDGE_STEP
