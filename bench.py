@@ -180,6 +180,16 @@ def run_simu_sff(pkg, dev):
             "note": "the 256x256 call is launch- and sync-bound (one 8-byte read per accept attempt); NOT the headline"}
 
 
+def _cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.lower().startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
 def _traffic():
     """DRAM bytes per launch from the committed `ncu --set full` captures (profiles/traffic_r1.json)."""
     path = os.path.join(ROOT, "profiles", "traffic_r1.json")
@@ -248,7 +258,8 @@ def run_reference_arm(args):
         "config": {"workload": "c3_train_step (bounded CPU sample: one 256x256 section per step; linear in pixels)",
                    "note": "the reference's sepconv is GPU-only (libs/sepconv/SeparableConvolution.py:47-48); per BASELINE.json "
                            "the CPU arm is an unfold-based torch-CPU evaluation of the same filter on all host cores"},
-        "cpu_baseline": {"value": round(val, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": round(val, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "cpu_model": _cpu_model(), "torch_threads": cores},
         "e2e": {"value": round(val, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -455,7 +466,8 @@ def run_gpu_arm(args):
                    "taps": [B, K, H, W], "pixels_per_step_per_gpu": pix_per_step, "parallelism": f"dp{world} (batch shards, no data-path collective; outputs gathered to rank 0 on a side stream)",
                    "l2": "working set 7 GB per step >> 126 MB L2 (no flush needed)"},
         "roofline": roof, "rooflines": rooflines,
-        "cpu_baseline": {"value": round(cpu_val, 4), "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": cpu_sample},
+        "cpu_baseline": {"value": round(cpu_val, 4), "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": cpu_sample,
+                         "cpu_model": _cpu_model(), "torch_threads": os.cpu_count()},
         "e2e": e2e, "gpu_launches": int(lsum.item()), "clocks": clocks,
         "extra": {"fwd_mpix_per_s": round(px_call / (fwd_ms * 1e-3) / 1e6, 1), "bwd_taps_mpix_per_s": round(px_call / (bwd_ms * 1e-3) / 1e6, 1),
                   "warp": warp, "gray_x3_shortcut": gray, "fused_interp_tail": tail, "simu_sff_c1": simu, "ms_per_step_by_rank": per_rank},
