@@ -10,7 +10,10 @@ import ctypes
 import os
 import threading
 
-from ._build import LIB_PATH as _DEFAULT_LIB_PATH
+from ._build import LIB_PATH as _DEFAULT_LIB_PATH, needs_build as _needs_build
+
+#: must equal SSTEM_ABI_VERSION of include/sstem_b200.h (checked against the loaded library in load())
+ABI_VERSION = 2
 
 #: SSTEM_LIB_PATH selects another build of the same library (kernel-tuning experiments)
 LIB_PATH = os.environ.get("SSTEM_LIB_PATH") or _DEFAULT_LIB_PATH
@@ -87,6 +90,13 @@ def load() -> ctypes.CDLL:
         lib.sstem_abi_version.restype = ctypes.c_int
         lib.sstem_error_string.argtypes = [ctypes.c_int]
         lib.sstem_error_string.restype = ctypes.c_char_p
+        got = int(lib.sstem_abi_version())
+        if got != ABI_VERSION:
+            raise SstemError(f"{LIB_PATH} exports ABI version {got}, this package binds version {ABI_VERSION}: "
+                             "stale library -- rebuild with `python -c 'import __graft_entry__ as g; g.build()'`")
+        if LIB_PATH == _DEFAULT_LIB_PATH and _needs_build(LIB_PATH):
+            import warnings
+            warnings.warn(f"{LIB_PATH} is older than its sources (csrc/ or include/sstem_b200.h): rebuild it", RuntimeWarning)
         _lib = lib
     return _lib
 

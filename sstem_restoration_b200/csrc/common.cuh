@@ -46,6 +46,15 @@ inline int sm_count() {
 
 inline int finish_launch() { return (int)cudaGetLastError(); }
 
+// One bit per device ordinal: "this kernel's function attributes have been set on that device".
+// Replica threads (nn.DataParallel) race here, so the flag is atomic; setting an attribute twice is
+// harmless, skipping it is not -- ordinals >= 64 simply set it on every call.
+struct PerDeviceOnce {
+    std::atomic<uint64_t> mask{0};
+    bool test(int dev) const { return dev < 64 && ((mask.load(std::memory_order_acquire) >> dev) & 1u); }
+    void set(int dev) { if (dev < 64) mask.fetch_or(uint64_t(1) << dev, std::memory_order_release); }
+};
+
 // ---- launchers implemented in the per-op translation units -----------------
 int launch_sepconv_fwd_generic(const float* in, const float* v, const float* h, float* out,
                                int64_t B, int64_t C, int64_t H, int64_t W, int K, bool strict,

@@ -1040,14 +1040,14 @@ interp_tail_fwd_k51_kernel(const __grid_constant__ TailFrames fa, int64_t frame_
 
 // ---- host side ------------------------------------------------------------------------------
 template <typename Kern>
-int set_smem_once(Kern kern, size_t smem, bool* done) {
+int set_smem_once(Kern kern, size_t smem, PerDeviceOnce& done) {
     int dev = 0;
     cudaGetDevice(&dev);
-    if (!done[dev & 15]) {
+    if (!done.test(dev)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        done[dev & 15] = true;
+        done.set(dev);
     }
     return 0;
 }

@@ -33,10 +33,10 @@ int launch_bwd_variant(const float* g, const float* in, const float* v, const fl
                        int64_t B, int C, int c0, int H, int W, int accumulate, int replicas, cudaStream_t s) {
     constexpr int G = SSTEM_BWD_G, R = SSTEM_BWD_R;
     constexpr size_t smem = smem_bytes<G, R, CC>();
-    static bool done[16] = {};
+    static PerDeviceOnce done;
     dim3 grid((unsigned)((W + Geo<G, R>::TILE_W - 1) / Geo<G, R>::TILE_W), (unsigned)((H + R - 1) / R), (unsigned)B);
     if (accumulate) {
-        static bool done_a[16] = {};
+        static PerDeviceOnce done_a;
         auto kern = sepconv_bwd_taps_k51_kernel<CC, G, R, VEC, PAIR, WV, WH, true>;
         if (int e = set_smem_once(kern, smem, done_a)) return e;
         kern<<<grid, 128, smem, s>>>(g, in, v, h, gv, gh, C, c0, H, W, replicas, (int64_t)0, 1, 1, 1.f);

@@ -9,7 +9,7 @@ int launch_fwd_variant(const float* in, const float* v, const float* h, float* o
                        int64_t B, int C, int c0, int H, int W, int replicas, cudaStream_t s) {
     constexpr int G = SSTEM_FWD_G, R = SSTEM_FWD_R;
     constexpr size_t smem = smem_bytes<G, R, CC>();
-    static bool done[16] = {};
+    static PerDeviceOnce done;
     auto kern = sepconv_fwd_k51_kernel<CC, G, R, VEC, PAIR>;
     if (int e = set_smem_once(kern, smem, done)) return e;
     dim3 grid((unsigned)((W + Geo<G, R>::TILE_W - 1) / Geo<G, R>::TILE_W), (unsigned)((H + R - 1) / R), (unsigned)B);

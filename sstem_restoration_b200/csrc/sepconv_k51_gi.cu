@@ -18,7 +18,7 @@ int launch_sepconv_bwd_input_k51(const float* g, const float* v, const float* h,
 #define SSTEM_GI_LAUNCH(CC_, VEC_)                                                                   \
     {                                                                                                 \
         constexpr size_t smem = smem_bytes<G, R, CC_>();                                              \
-        static bool done[16] = {};                                                                    \
+        static PerDeviceOnce done;                                                                    \
         auto kern = sepconv_bwd_input_k51_kernel<CC_, R, VEC_>;                                    \
         if (int err = set_smem_once(kern, smem, done)) return err;                                    \
         kern<<<grid, 128, smem, s>>>(g, v, h, gi, (int)C, c0, (int)H, (int)W);                        \

@@ -17,12 +17,12 @@ int launch_interp_tail_fwd_k51(const float* frame1, const float* frame2, int64_t
     dim3 grid((unsigned)((W + Geo<G, R>::TILE_W - 1) / Geo<G, R>::TILE_W), (unsigned)((H + R - 1) / R), (unsigned)B);
     const TailFrames fa = {{frame2, frame1}, {k2v, k1v}, {k2h, k1h}};   // frame 2 first, as the reference's expression
     if (vec) {
-        static bool done[16] = {};
+        static PerDeviceOnce done;
         auto kern = interp_tail_fwd_k51_kernel<G, R, true>;
         if (int e = set_smem_once(kern, smem, done)) return e;
         kern<<<grid, 128, smem_used, s>>>(fa, frame_bstride, cs, nplanes, out, scale, (int)H, (int)W);
     } else {
-        static bool done[16] = {};
+        static PerDeviceOnce done;
         auto kern = interp_tail_fwd_k51_kernel<G, R, false>;
         if (int e = set_smem_once(kern, smem, done)) return e;
         kern<<<grid, 128, smem_used, s>>>(fa, frame_bstride, cs, nplanes, out, scale, (int)H, (int)W);
@@ -39,7 +39,7 @@ int launch_tail_bwd_variant(const float* g, const float* frame, int64_t frame_bs
     constexpr size_t smem = smem_bytes<G, R, 3>();          // up to 3 channel planes are staged side by side
     const int nplanes = cs <= 3 ? cs : 1;
     const size_t smem_used = nplanes == 1 ? smem_bytes<G, R, 1>() : (nplanes == 2 ? smem_bytes<G, R, 2>() : smem);
-    static bool done[16] = {};
+    static PerDeviceOnce done;
     auto kern = sepconv_bwd_taps_k51_kernel<1, G, R, VEC, false, WV, WH, false, true>;
     if (int e = set_smem_once(kern, smem, done)) return e;
     dim3 grid((unsigned)((W + Geo<G, R>::TILE_W - 1) / Geo<G, R>::TILE_W), (unsigned)((H + R - 1) / R), (unsigned)B);

@@ -401,13 +401,13 @@ static int try_launch_warp_tma(const float* moving, const float* flow, const int
     if (!make_map3(&mims, moving, W, H, B * CT, W, H * W, WT_SW, WT_SH, CT)) return -1000;
     if (!make_map3(&mimm, moving, W, H, B * CT, W, H * W, WT_MW, WT_MH, CT)) return -1000;
     const size_t smem = (size_t)(CT * WT_BH * WT_BW + 2 * WT_TH * WT_TW) * sizeof(float) + 64;
-    static bool done[16] = {};
+    static PerDeviceOnce done;
     int dev = 0;
     cudaGetDevice(&dev);
-    if (!done[dev & 15]) {
+    if (!done.test(dev)) {
         cudaError_t e = cudaFuncSetAttribute(warp_torch_tma_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        done[dev & 15] = true;
+        done.set(dev);
     }
     dim3 grid((unsigned)((W + WT_TW - 1) / WT_TW), (unsigned)((H + WT_TH - 1) / WT_TH), (unsigned)B);
     warp_torch_tma_kernel<CT><<<grid, WT_THREADS, smem, s>>>(mfx, mfy, mim, mims, mimm, moving, out, (int)H, (int)W);
@@ -430,10 +430,19 @@ image_warp_kernel(const PixT* __restrict__ im, const float* __restrict__ flow,
     const int nc = CT > 0 ? CT : C;
     const bool full = idx0 + PX <= total;
     float fx[PX], fy[PX];
-    if (full) {                                          // 32 bytes of flow, 32-byte aligned
+    // idx0 is a multiple of 4, so flow + 2*idx0 is 32-byte aligned exactly when the flow base is 16-byte aligned;
+    // an 8-byte aligned base (the ABI minimum: e.g. flows[i] of a [N,H,W,2] tensor with H*W odd) takes 8-byte loads
+    const bool flow16 = (reinterpret_cast<uintptr_t>(flow) & 15u) == 0;
+    if (full && flow16) {
         const float4 a = __ldcs(reinterpret_cast<const float4*>(flow + 2 * idx0));
         const float4 c = __ldcs(reinterpret_cast<const float4*>(flow + 2 * idx0) + 1);
         fx[0] = a.x; fy[0] = a.y; fx[1] = a.z; fy[1] = a.w; fx[2] = c.x; fy[2] = c.y; fx[3] = c.z; fy[3] = c.w;
+    } else if (full) {
+#pragma unroll
+        for (int p = 0; p < PX; ++p) {
+            const float2 f = __ldcs(reinterpret_cast<const float2*>(flow + 2 * (idx0 + p)));
+            fx[p] = f.x; fy[p] = f.y;
+        }
     } else {
 #pragma unroll
         for (int p = 0; p < PX; ++p) {

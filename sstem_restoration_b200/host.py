@@ -10,6 +10,7 @@ PCIe link runs full duplex and the kernels disappear behind it.  Semantics are t
 """
 from __future__ import annotations
 
+import threading
 from typing import Optional, Tuple
 
 import torch
@@ -37,14 +38,18 @@ class _Workspace:
 
 _streams = {}
 _workspaces = {}
+_res_lock = threading.Lock()
 
 
 def _resources(device, n):
-    key = (device.index, n)
-    if key not in _streams:
-        _streams[key] = [torch.cuda.Stream(device=device) for _ in range(n)]
-        _workspaces[key] = [_Workspace(device) for _ in range(n)]
-    return _streams[key], _workspaces[key]
+    """Side streams + staging buffers of (calling thread, device): replica threads (nn.DataParallel) never share
+    a workspace, so two concurrent calls cannot overwrite each other's staging buffers."""
+    key = (threading.get_ident(), device.index, n)
+    with _res_lock:
+        if key not in _streams:
+            _streams[key] = [torch.cuda.Stream(device=device) for _ in range(n)]
+            _workspaces[key] = [_Workspace(device) for _ in range(n)]
+        return _streams[key], _workspaces[key]
 
 
 def sepconv_forward_backward_host(input: torch.Tensor, vertical: torch.Tensor, horizontal: torch.Tensor,
@@ -53,9 +58,11 @@ def sepconv_forward_backward_host(input: torch.Tensor, vertical: torch.Tensor, h
                                   out: Optional[Tuple[torch.Tensor, ...]] = None, join: bool = True):
     """input [B,C,H+50,W+50], vertical/horizontal [B,51,H,W], grad_output [B,C,H,W]: CPU float32,
     ideally pinned.  Returns CPU (pinned) ``output`` or ``(output, grad_vertical, grad_horizontal)``.
-    ``out`` may supply the pinned result tensors to reuse.  With ``join=False`` the call only queues
-    the work (back-to-back calls then overlap one call's downloads with the next call's uploads);
-    call :func:`join_host_pipeline` (or synchronize the device) before reading the results."""
+    ``out`` may supply the pinned result tensors to reuse.  With ``join=True`` (default) the call returns
+    after the last device->host copy has COMPLETED (host-side synchronisation of the side streams): the
+    returned CPU tensors can be read immediately.  With ``join=False`` the call only queues the work
+    (back-to-back calls then overlap one call's downloads with the next call's uploads); the CPU results
+    are NOT valid until :func:`join_host_pipeline` (or a device synchronize) has returned."""
     if not torch.cuda.is_available():
         raise _lib.SstemError("sepconv_forward_backward_host: no CUDA device; there is no CPU fallback")
     for t in (input, vertical, horizontal):
@@ -110,10 +117,17 @@ def sepconv_forward_backward_host(input: torch.Tensor, vertical: torch.Tensor, h
     return tuple(res) if want_grad else res[0]
 
 
-def join_host_pipeline(device=None, n_streams: int = 3) -> None:
-    """Make the current stream wait for everything queued by sepconv_forward_backward_host."""
+def join_host_pipeline(device=None, n_streams: int = 3, host_sync: bool = True) -> None:
+    """Wait for everything this thread queued with sepconv_forward_backward_host on `device`.
+
+    ``host_sync=True`` (default): block the calling host thread until the side streams have drained -- the
+    pinned CPU results are then complete and safe to read.  ``host_sync=False``: only make the current CUDA
+    stream wait for the side streams (a device-side dependency; the host is NOT blocked and CPU results must
+    not be read yet) -- for callers that keep queueing device work behind the results."""
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     streams, _ = _resources(dev, n_streams)
     cur = torch.cuda.current_stream(dev)
     for s in streams:
         cur.wait_stream(s)
+        if host_sync:
+            s.synchronize()

@@ -86,6 +86,21 @@ def _check_shapes(input, vertical, horizontal, filter_size=None):
     return intFilterSize, intOutputHeight, intOutputWidth
 
 
+def _check_grad_output(grad_output, shape, like):
+    """The kernels read the upstream gradient as contiguous float32 on the op's device: anything else
+    (AMP half gradients, a double gradient handed to .backward(), another device) is converted or refused
+    here instead of being misread."""
+    if tuple(grad_output.shape) != tuple(shape):
+        raise ValueError(f"sepconv backward: grad_output has shape {tuple(grad_output.shape)}, expected {tuple(shape)}")
+    if grad_output.device != like.device:
+        raise ValueError(f"sepconv backward: grad_output is on {grad_output.device}, the op ran on {like.device}")
+    if grad_output.dtype != torch.float32:
+        if not grad_output.dtype.is_floating_point:
+            raise TypeError(f"sepconv backward: grad_output dtype {grad_output.dtype} is not a floating type")
+        grad_output = grad_output.to(torch.float32)
+    return grad_output.contiguous()
+
+
 def _forward_impl(ctx, input, vertical, horizontal, filter_size):
     K, oh, ow = _check_shapes(input, vertical, horizontal, filter_size)
     if input.is_cuda == False:
@@ -116,9 +131,9 @@ def _backward_impl(ctx, grad_output):
     need_in, need_v, need_h = ctx.needs_input_grad[:3]
     B, C = input.size(0), input.size(1)
     K, oh, ow = vertical.size(1), vertical.size(2), vertical.size(3)
-    grad_output = grad_output.contiguous()
     if grad_output.is_cuda == False:
         raise NotImplementedError()
+    grad_output = _check_grad_output(grad_output, (B, C, oh, ow), input)
     grad_input = torch.empty_like(input) if need_in else None
     grad_vertical = torch.empty_like(vertical) if need_v else None
     grad_horizontal = torch.empty_like(horizontal) if need_h else None
@@ -228,7 +243,9 @@ class _InterpolationTail(torch.autograd.Function):
                                       "(use SeparableConvolution on the padded frames for that)")
         need = ctx.needs_input_grad[2:6]
         B, C, H, W = i1.shape
-        grad_output = grad_output.contiguous()
+        if grad_output.is_cuda == False:
+            raise NotImplementedError()
+        grad_output = _check_grad_output(grad_output, (B, 1, H, W), i1)
         grads = [torch.empty_like(k) if n else None for k, n in zip((k1v, k1h, k2v, k2h), need)]
         if any(need) and grad_output.numel() > 0:
             code = _lib.load().sstem_interp_tail_backward(

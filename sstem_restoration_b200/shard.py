@@ -37,8 +37,9 @@ def max_units_per_rank(n_units: int, world_size: int) -> int:
 def gather_sections(local: torch.Tensor, n_units: int, group=None, dst=None):
     """Gather the per-rank outputs [n_local, ...] into [n_units, ...] in unit order.
 
-    ``dst=None``: every rank gets the result (one all_gather_into_tensor).  ``dst=r``: only rank
-    ``r`` does (what nn.DataParallel's output gather does in the reference, main_ms.py:97-103);
+    ``dst=None``: every rank gets the result (one all_gather_into_tensor).  ``dst=r``: only the rank
+    whose rank INSIDE ``group`` is ``r`` does (group-local, like ``rank``; translated to the global rank
+    torch.distributed.gather expects) (what nn.DataParallel's output gather does in the reference, main_ms.py:97-103);
     the other ranks return None -- 1/world_size of the traffic.
     Ranks may hold different counts (n_units % world_size != 0): each rank pads to
     the maximum, padding is dropped on arrival.
@@ -46,7 +47,7 @@ def gather_sections(local: torch.Tensor, n_units: int, group=None, dst=None):
     if not (dist.is_available() and dist.is_initialized()):
         return local
     ws = dist.get_world_size(group)
-    rank = dist.get_rank(group)
+    rank = dist.get_rank(group)                          # group-local rank; `dst` is group-local too
     lo, hi = shard_range(n_units, rank, ws)
     if local.shape[0] != hi - lo:
         raise ValueError(f"rank {rank} holds {local.shape[0]} units, expected {hi - lo}")
@@ -62,7 +63,8 @@ def gather_sections(local: torch.Tensor, n_units: int, group=None, dst=None):
             # (on 8 GPUs those copies cost rank 0 -- and through the collective everybody -- 8 % of the step)
             out = torch.empty((ws * m,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
             bufs = list(out.split(m, 0))
-        dist.gather(padded.contiguous(), bufs, dst=dst, group=group)
+        gdst = dist.get_global_rank(group, dst) if group is not None else dst
+        dist.gather(padded.contiguous(), bufs, dst=gdst, group=group)
         if rank != dst:
             return None
     else:

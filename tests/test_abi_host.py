@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol(built_lib):
 def test_abi_version_and_error_strings(built_lib):
     from sstem_restoration_b200 import _lib
     lib = _lib.load()
-    assert lib.sstem_abi_version() == 1
+    assert lib.sstem_abi_version() == _lib.ABI_VERSION
     assert lib.sstem_error_string(0) == b"success"
     for code in (-1, -2, -3, -4, -5):
         assert lib.sstem_error_string(code).startswith(b"sstem:")
