@@ -137,3 +137,22 @@ def test_image_warp_identity_at_full_size():
     flow[..., 0] = 5.0
     got = image_warp(im, flow)
     assert torch.equal(got[:, :-5], im[:, 5:]) and torch.equal(got[:, -5:], im[:, -1:].expand(-1, 5))
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.float32])
+def test_image_warp_flow_slice_that_is_only_8_byte_aligned(dtype):
+    """flows[i] of a [N,H,W,2] tensor with H*W odd starts 8 (not 16) bytes into a 16-byte line: the ABI's minimum flow
+    alignment.  The kernel must not take its 16-byte flow loads there (it used to fault with 'misaligned address')."""
+    from sstem_restoration_b200.warp import _image_warp_cuda
+    r = np.random.default_rng(78)
+    H, W = 33, 47                                         # H*W odd
+    ims = r.integers(0, 256, (3, H, W, 3)).astype(dtype)
+    flows = (4.0 * r.standard_normal((3, H, W, 2))).astype(np.float32)
+    t_im, t_fl = torch.from_numpy(ims).cuda(), torch.from_numpy(flows).cuda()
+    assert t_fl[1].data_ptr() % 16 == 8 and t_fl[1].is_contiguous()
+    for i in range(3):
+        u8, f = _image_warp_cuda(t_im[i], t_fl[i], "bilinear", want_float=True)
+        ref_u8, ref_f = oracle.image_warp_restated(ims[i], flows[i], "bilinear", return_float=True)
+        assert np.array_equal(u8.cpu().numpy(), ref_u8)
+        assert np.array_equal(_bits(f.cpu().numpy()), _bits(ref_f.astype(np.float32)))
+    torch.cuda.synchronize()
