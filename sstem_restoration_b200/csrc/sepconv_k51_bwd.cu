@@ -16,6 +16,9 @@ int launch_bwd_taps_k51_v(const float* g, const float* in, const float* v, const
 int launch_bwd_taps_k51_h(const float* g, const float* in, const float* v, const float* h, float* gv, float* gh,
                           int64_t B, int C, int H, int W, bool gray, cudaStream_t s);
 
+int try_launch_bwd_taps_k51_v2(const float* g, const float* in, const float* v, const float* h, float* gv, float* gh,
+                               int64_t B, int C, int c0, int H, int W, int accumulate, cudaStream_t s);
+
 #if SSTEM_BWD_PART == 0
 int launch_sepconv_bwd_taps_k51(const float* g, const float* in, const float* v, const float* h,
                                 float* gv, float* gh, int64_t B, int64_t C, int64_t H, int64_t W, bool gray, cudaStream_t s) {
@@ -70,7 +73,11 @@ int launch_bwd_all(const float* g, const float* in, const float* v, const float*
         const int cc = (C - c0) < 3 ? (C - c0) : 3;
         const int acc = c0 > 0;
         int e;
-        if (cc == 3) e = launch_bwd_chunk<3, WV, WH>(g, in, v, h, gv, gh, B, C, c0, H, W, acc, 1, s);
+        if (cc == 3) {
+            // second-generation kernel (TMA-staged, channel-interleaved window) when its layout rules hold
+            e = try_launch_bwd_taps_k51_v2(g, in, v, h, WV ? gv : nullptr, WH ? gh : nullptr, B, C, c0, H, W, acc, s);
+            if (e == -1000) e = launch_bwd_chunk<3, WV, WH>(g, in, v, h, gv, gh, B, C, c0, H, W, acc, 1, s);
+        }
         else if (cc == 2) e = launch_bwd_chunk<2, WV, WH>(g, in, v, h, gv, gh, B, C, c0, H, W, acc, 1, s);
         else e = launch_bwd_chunk<1, WV, WH>(g, in, v, h, gv, gh, B, C, c0, H, W, acc, 1, s);
         if (e) return e;

@@ -1,0 +1,330 @@
+// Third-generation tap-gradient kernel: persistent warps fed entirely by TMA.
+//
+// Measured on the second generation (sepconv_k51_v2.cuh; ncu, profiles/): with the window and the vertical taps of a
+// tile arriving as two big TMA boxes the step loop itself became 15 % faster, but the tile's prologue -- waiting for
+// ~130 KB per tile to cross the SM's L2 port, then for the horizontal taps -- grew to 16 % of all warp time, because a
+// CTA cannot prefetch its next tile and only one other CTA is there to cover.  Here nothing waits:
+//
+//   * a WARP, not a CTA, owns a tile (8 columns x 4 rows) and walks a sequence of tiles (persistent grid, two
+//     4-warp CTAs per SM); warps never synchronise with each other, so they drift apart and cover each other's
+//     tile switches;
+//   * the window streams through a 3-slot ring in groups of 4 input rows: one TMA box {4 channels, 60 columns, 4 rows}
+//     of the channel-interleaved input (see v2) plus one box {8 columns, 4 rows, 4 planes} of vertical taps per group,
+//     requested two groups (8 steps) ahead by lane 0, completion on the slot's mbarrier.  A step's vertical taps sit
+//     in the current or the previous group's slot at compile-time offsets; tap planes outside 0..50 and pixels
+//     outside the image are zero-filled by the TMA unit;
+//   * the horizontal taps and the upstream gradient of the NEXT tile are prefetched into shared memory by two more
+//     boxes issued right after the current tile copied its own into registers, a whole tile (~30 us) ahead.
+//
+// Per step a lane issues 130 FFMA2, 13 LDS.128 (window), 4 LDS (v), the gv transpose-reduce and one store; the
+// ring costs ~10 instructions per 4 steps.  Arithmetic (operation order) is that of generations 1 and 2: results
+// are bit-identical.
+#pragma once
+#include "sepconv_k51_v2.cuh"
+#include <type_traits>
+
+namespace sstem {
+namespace {
+
+constexpr int V3_COLS = 8;                                   // columns per warp tile
+constexpr int V3_WIN_COLS = 60;                              // 8 + 52 tap slots
+constexpr int V3_GROUP = 4;                                  // input rows per ring slot
+constexpr int V3_NGROUPS = 14;                               // 56 >= 54 input rows per tile
+constexpr unsigned V3_WIN_BYTES = V3_GROUP * V3_WIN_COLS * 16;   // 3840
+constexpr unsigned V3_V_BYTES = V3_GROUP * V2_R * V3_COLS * 4;   // 512: [plane][row][col]
+constexpr unsigned V3_SLOT_BYTES = V3_WIN_BYTES + V3_V_BYTES;    // 4352 = 34 * 128
+constexpr unsigned V3_H_BYTES = K51 * V2_R * V3_COLS * 4;        // 6528: [tap][row][col]
+constexpr unsigned V3_G_BYTES = 3 * V2_R * V3_COLS * 4;          // 384:  [channel][row][col]
+constexpr unsigned V3_OFF_H = 3 * V3_SLOT_BYTES;                 // 13056
+constexpr unsigned V3_OFF_G = V3_OFF_H + V3_H_BYTES;             // 19584
+constexpr unsigned V3_OFF_BAR = V3_OFF_G + V3_G_BYTES;           // 19968: full[3], hbar
+constexpr unsigned V3_WARP_BYTES = V3_OFF_BAR + 128;             // 20096 = 157 * 128
+constexpr int V3_WARPS = 4;
+constexpr size_t V3_SMEM = (size_t)V3_WARPS * V3_WARP_BYTES + 128;
+
+struct V3Shape {
+    int H, W, tiles_x, tiles_y, ntiles, C, c0;
+};
+
+__device__ __forceinline__ void mbar_expect_tx_a(unsigned bar_addr, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(unsigned bar_addr, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"(bar_addr), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_a(unsigned dst, const CUtensorMap* map, unsigned bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_a(unsigned dst, const CUtensorMap* map, unsigned bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ float lds_f32(unsigned addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float4 lds_f32x4(unsigned addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
+// One input row; same arithmetic as bwd2_step, operands addressed by shared-memory byte addresses:
+//   pa            window row of this step, already offset to the lane's first tap column
+//   va[p]         address of v[fy = s - p][row p][column of the lane]   (only read when the row is active)
+template <int S, bool WV, bool WH>
+__device__ __forceinline__ void bwd3_step(unsigned pa, const unsigned (&va)[4], bool novalid,
+                                          const float2 (&g2)[3][2], const float2 (&h2)[2][13],
+                                          float2 (&gh2)[2][13], float2 (&gvp)[2]) {
+    constexpr int NP = 2, NT = 13;
+    float2 v2[NP];
+#pragma unroll
+    for (int pp = 0; pp < NP; ++pp) {
+        // S >= 0: a row whose fy = S - p is outside 0..50 gets v = 0 without touching shared memory
+        const bool a_ok = (S < 0) || (S - 2 * pp >= 0 && S - 2 * pp < K51);
+        const bool b_ok = (S < 0) || (S - 2 * pp - 1 >= 0 && S - 2 * pp - 1 < K51);
+        v2[pp].x = (WH && a_ok) ? lds_f32(va[2 * pp]) : 0.f;
+        v2[pp].y = (WH && b_ok) ? lds_f32(va[2 * pp + 1]) : 0.f;
+    }
+    float2 gva[NP], gvb[NP];
+#pragma unroll
+    for (int pp = 0; pp < NP; ++pp) gva[pp] = gvb[pp] = make_float2(0.f, 0.f);
+    float2 t2[NT][NP];
+    float4 P[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+        P[t] = lds_f32x4(pa + 64 * t);                     // channels x, y, z of column x + g + 4t
+        if (t == NT - 1) {                                 // tap 51 does not exist (lanes g == 3)
+            P[t].x = novalid ? 0.f : P[t].x;
+            P[t].y = novalid ? 0.f : P[t].y;
+            P[t].z = novalid ? 0.f : P[t].z;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int t = 0; t < NT; ++t)
+#pragma unroll
+            for (int pp = 0; pp < NP; ++pp) {
+                if (S >= 0 && (S < 2 * pp || S > 2 * pp + K51)) continue;
+                const float p = c == 0 ? P[t].x : (c == 1 ? P[t].y : P[t].z);
+                t2[t][pp] = __ffma2_rn(make_float2(p, p), g2[c][pp], c == 0 ? make_float2(0.f, 0.f) : t2[t][pp]);
+            }
+#pragma unroll
+    for (int t = 0; t < NT; ++t)
+#pragma unroll
+        for (int pp = 0; pp < NP; ++pp) {
+            if (S >= 0) {
+                if (S < 2 * pp || S > 2 * pp + K51) continue;
+                if (S - 2 * pp > K51 - 1) t2[t][pp].x = 0.f;
+                if (S - 2 * pp - 1 < 0) t2[t][pp].y = 0.f;
+            }
+            if (WH) gh2[pp][t] = __ffma2_rn(t2[t][pp], v2[pp], gh2[pp][t]);
+            if (WV) {
+                if (t & 1) gvb[pp] = __ffma2_rn(t2[t][pp], h2[pp][t], gvb[pp]);
+                else gva[pp] = __ffma2_rn(t2[t][pp], h2[pp][t], gva[pp]);
+            }
+        }
+#pragma unroll
+    for (int pp = 0; pp < NP; ++pp) gvp[pp] = make_float2(gva[pp].x + gvb[pp].x, gva[pp].y + gvb[pp].y);
+}
+
+template <bool WV, bool WH, bool ACCUM>
+__global__ void __launch_bounds__(V3_WARPS * 32, 2)
+sepconv_bwd_taps_k51_v3_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_v,
+                               const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_g,
+                               float* __restrict__ gv, float* __restrict__ gh, int* __restrict__ next_tile_counter,
+                               const V3Shape sh) {
+    constexpr int G = 4, R = 4, NP = 2, NT = 13;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pg = lane / G, g = lane % G;
+    const bool novalid = (g == 3);
+    const bool lead = (lane == 0);
+    // Tiles are handed out dynamically (one atomic per warp and tile): warps do not run at the same speed (L2 distance,
+    // DRAM refresh, the other warp on the scheduler), and with a static round-robin the kernel waited for the slowest warp
+    // while 14 % of the warp slots sat empty (ncu: warps_active 6.9 of 8).  The first two tiles of a warp are static, so
+    // the prefetch of the next tile's taps never waits for an atomic: the ticket drawn at the start of tile k is tile k+2.
+    const int nwarps = gridDim.x * V3_WARPS;
+    int tile = blockIdx.x * V3_WARPS + warp;
+    if (tile >= sh.ntiles) return;
+    int ntile = tile + nwarps;
+
+    const unsigned base = ((unsigned)__cvta_generic_to_shared(smem_raw) + 127u & ~127u) + warp * V3_WARP_BYTES;
+    const unsigned bar0 = base + V3_OFF_BAR;               // full[slot] at bar0 + 8 * slot, hbar at bar0 + 24
+    const unsigned hbar = bar0 + 24;
+    if (lead) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8 * i), "r"(1));
+        mbar_fence_init();
+    }
+    __syncwarp();
+
+    const int64_t plane = (int64_t)sh.H * sh.W;
+    auto decode = [&](int t, int& b, int& y0, int& x0) {
+        const int tx = t % sh.tiles_x, r = t / sh.tiles_x;
+        x0 = tx * V3_COLS;
+        y0 = (r % sh.tiles_y) * R;
+        b = r / sh.tiles_y;
+    };
+    // ring slots travel in registers: slot byte address, its barrier address and the parity of its next completion
+    unsigned s_cur = base, s_nxt = base + V3_SLOT_BYTES, s_prv = base + 2 * V3_SLOT_BYTES;
+    unsigned b_cur = bar0, b_nxt = bar0 + 8, b_prv = bar0 + 16;
+    unsigned p_cur = 0, p_nxt = 0, p_prv = 0, p_h = 0;
+    auto issue_group = [&](unsigned slot, unsigned bar, int b, int y0, int x0, int gi) {
+        if (lead) {
+            mbar_expect_tx_a(bar, V3_WIN_BYTES + (WH ? V3_V_BYTES : 0u));
+            tma_load_3d_a(slot, &map_in, bar, 4 * x0, y0 + V3_GROUP * gi, b);   // rows of 60 pixels x 4 floats: 960 contiguous bytes
+            if (WH) tma_load_4d_a(slot + V3_WIN_BYTES, &map_v, bar, x0, y0, V3_GROUP * gi, b);
+        }
+    };
+    auto issue_hg = [&](int b, int y0, int x0) {
+        if (lead) {
+            mbar_expect_tx_a(hbar, (WV ? V3_H_BYTES : 0u) + V3_G_BYTES);
+            if (WV) tma_load_4d_a(base + V3_OFF_H, &map_h, hbar, x0, y0, 0, b);
+            tma_load_4d_a(base + V3_OFF_G, &map_g, hbar, x0, y0, 0, b);
+        }
+    };
+    auto rotate = [&]() {                                  // (cur, nxt, prv) <- (nxt, prv, cur)
+        unsigned t;
+        t = s_cur; s_cur = s_nxt; s_nxt = s_prv; s_prv = t;
+        t = b_cur; b_cur = b_nxt; b_nxt = b_prv; b_prv = t;
+        t = p_cur; p_cur = p_nxt; p_nxt = p_prv; p_prv = t;
+    };
+
+    int tb, ty0, tx0;
+    decode(tile, tb, ty0, tx0);
+    issue_hg(tb, ty0, tx0);
+    issue_group(s_cur, b_cur, tb, ty0, tx0, 0);
+    issue_group(s_nxt, b_nxt, tb, ty0, tx0, 1);
+
+    const unsigned lane_win = (unsigned)(pg + g) * 16u;    // lane's first tap column inside a window row
+    const unsigned lane_v = V3_WIN_BYTES + (unsigned)pg * 4u;
+
+#pragma unroll 1
+    for (;;) {
+        const bool has_next = ntile < sh.ntiles;
+        int nb = 0, ny0 = 0, nx0 = 0;
+        if (has_next) decode(ntile, nb, ny0, nx0);
+        int ticket = 0;
+        if (has_next && lead) ticket = atomicAdd(next_tile_counter, 1);   // consumed at the end of this tile
+
+        // ---- this tile's horizontal taps and upstream gradient: shared memory -> registers
+        float2 h2[NP][NT], gh2[NP][NT], g2[3][NP];
+        mbar_wait_a(hbar, p_h);
+        p_h ^= 1;
+        {
+            const unsigned ha = base + V3_OFF_H + (unsigned)pg * 4u;
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                const int tap = (t == NT - 1 && novalid) ? (G * (NT - 2) + g) : (G * t + g);   // tap 51: reread tap 47 (masked by P = 0)
+#pragma unroll
+                for (int pp = 0; pp < NP; ++pp) {
+                    gh2[pp][t] = make_float2(0.f, 0.f);
+                    h2[pp][t] = WV ? make_float2(lds_f32(ha + ((tap * R + 2 * pp) * V3_COLS) * 4),
+                                                 lds_f32(ha + ((tap * R + 2 * pp + 1) * V3_COLS) * 4))
+                                   : make_float2(0.f, 0.f);
+                }
+            }
+            const unsigned ga = base + V3_OFF_G + (unsigned)pg * 4u;
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int pp = 0; pp < NP; ++pp)
+                    g2[c][pp] = make_float2(lds_f32(ga + ((c * R + 2 * pp) * V3_COLS) * 4), lds_f32(ga + ((c * R + 2 * pp + 1) * V3_COLS) * 4));
+        }
+        __syncwarp();                                      // every lane has its copy: the buffers may be refilled
+        if (has_next) issue_hg(nb, ny0, nx0);
+
+        const int x = tx0 + pg;
+        const bool col_ok = x < sh.W;
+        float* gv_ptr = WV ? gv + (int64_t)tb * K51 * plane + (int64_t)min(ty0 + g, sh.H - 1) * sh.W + min(x, sh.W - 1) - (int64_t)g * plane
+                           : nullptr;
+        const bool gv_row_ok = col_ok && (ty0 + g < sh.H);
+        float2 gvp[NP];
+        auto store_gv = [&](int fy) {                      // fy = s - g for this lane
+            if (WV) {
+                float val[R];
+#pragma unroll
+                for (int pp = 0; pp < NP; ++pp) { val[2 * pp] = gvp[pp].x; val[2 * pp + 1] = gvp[pp].y; }
+                group_reduce<G, R>(val, g);                // lane g now holds the total of row g
+                if (gv_row_ok && fy >= 0 && fy < K51) *gv_ptr = ACCUM ? (*gv_ptr + val[0]) : val[0];
+                gv_ptr += plane;
+            }
+        };
+        // One group of 4 input rows.  GI >= 0: compile-time group index (first / last groups of the tile, whose steps
+        // are partially active); GI < 0: steady state, runtime group index gi.
+        auto run_step = [&](auto gi_tag, auto u_tag, int gi, unsigned wa, unsigned vc, unsigned vp) {
+            constexpr int GI = decltype(gi_tag)::value, U = decltype(u_tag)::value;
+            constexpr int S = GI < 0 ? -1 : GI * V3_GROUP + U;            // compile-time step of the partial groups
+            if (GI >= 0 && GI * V3_GROUP + U >= V2_WIN_H) return;         // rows 54, 55 of the last group: nothing to do
+            unsigned va[4];
+#pragma unroll
+            for (int p = 0; p < 4; ++p)                    // plane s - p: this group's slot or the previous one's
+                va[p] = (U - p >= 0 ? vc + ((U - p) * R + p) * V3_COLS * 4 : vp + ((V3_GROUP + U - p) * R + p) * V3_COLS * 4);
+            bwd3_step<S, WV, WH>(wa + U * V3_WIN_COLS * 16, va, novalid, g2, h2, gh2, gvp);
+            store_gv(V3_GROUP * gi + U - g);
+        };
+        auto run_group = [&](auto gi_tag, int gi) {
+            mbar_wait_a(b_cur, p_cur);
+            p_cur ^= 1;
+            const unsigned wa = s_cur + lane_win, vc = s_cur + lane_v, vp = s_prv + lane_v;
+            run_step(gi_tag, std::integral_constant<int, 0>{}, gi, wa, vc, vp);
+            run_step(gi_tag, std::integral_constant<int, 1>{}, gi, wa, vc, vp);
+            run_step(gi_tag, std::integral_constant<int, 2>{}, gi, wa, vc, vp);
+            run_step(gi_tag, std::integral_constant<int, 3>{}, gi, wa, vc, vp);
+        };
+        auto end_group = [&](bool next_tile, int gi_issue) {   // everyone is done with the previous group's slot: refill it
+            __syncwarp();
+            if (next_tile) { if (has_next) issue_group(s_prv, b_prv, nb, ny0, nx0, gi_issue); }
+            else issue_group(s_prv, b_prv, tb, ty0, tx0, gi_issue);
+            rotate();
+        };
+
+        run_group(std::integral_constant<int, 0>{}, 0);
+        end_group(false, 2);
+#pragma unroll 1
+        for (int gi = 1; gi < 12; ++gi) {                  // groups 1..11 = steps 4..47: every row active
+            run_group(std::integral_constant<int, -1>{}, gi);
+            end_group(false, gi + 2);
+        }
+        run_group(std::integral_constant<int, 12>{}, 12);  // steps 48..51
+        end_group(true, 0);
+        run_group(std::integral_constant<int, 13>{}, 13);  // steps 52, 53 (+ two rows nobody needs)
+        end_group(true, 1);
+
+        // ---- gh: complete per lane (the sum over fy happened in registers)
+        if (WH && col_ok) {
+            float* gp = gh + ((int64_t)tb * K51 + g) * plane + x;
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                if (t == NT - 1 && novalid) break;
+#pragma unroll
+                for (int pp = 0; pp < NP; ++pp) {
+                    const int ya = ty0 + 2 * pp, yb = ya + 1;
+                    float* da = gp + (int64_t)(G * t) * plane + (int64_t)ya * sh.W;
+                    float* db = gp + (int64_t)(G * t) * plane + (int64_t)yb * sh.W;
+                    if (ya < sh.H) *da = ACCUM ? (*da + gh2[pp][t].x) : gh2[pp][t].x;
+                    if (yb < sh.H) *db = ACCUM ? (*db + gh2[pp][t].y) : gh2[pp][t].y;
+                }
+            }
+        }
+        if (!has_next) break;
+        tile = ntile; tb = nb; ty0 = ny0; tx0 = nx0;
+        ntile = 2 * nwarps + __shfl_sync(0xffffffffu, ticket, 0);
+    }
+}
+
+}  // namespace
+}  // namespace sstem
