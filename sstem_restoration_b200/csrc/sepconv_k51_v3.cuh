@@ -147,7 +147,9 @@ sepconv_bwd_taps_k51_v3_kernel(const __grid_constant__ CUtensorMap map_in, const
                                const V3Shape sh) {
     constexpr int G = 4, R = 4, NP = 2, NT = 13;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // the shuffle tells the compiler that `warp` -- and with it every ring / barrier address and TMA coordinate below --
+    // is warp-uniform, so those live in uniform registers and a TMA issue needs no R2UR moves
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int pg = lane / G, g = lane % G;
     const bool novalid = (g == 3);
     const bool lead = (lane == 0);
