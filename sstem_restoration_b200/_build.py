@@ -26,6 +26,7 @@ UNITS = [
     ("sepconv_k51_bwd.cu", ["-DSSTEM_BWD_PART=2"], "_p2"),
     ("sepconv_k51_bwd.cu", ["-DSSTEM_BWD_PART=3"], "_p3"),
     ("sepconv_k51_bwd2.cu", [], ""),
+    ("sepconv_k51_fwd3.cu", [], ""),
     ("sepconv_k51_gi.cu", [], ""),
     ("sepconv_k51_tail.cu", [], ""),
     ("warp.cu", [], ""),

@@ -16,9 +16,6 @@ int launch_bwd_taps_k51_v(const float* g, const float* in, const float* v, const
 int launch_bwd_taps_k51_h(const float* g, const float* in, const float* v, const float* h, float* gv, float* gh,
                           int64_t B, int C, int H, int W, bool gray, cudaStream_t s);
 
-int try_launch_bwd_taps_k51_v2(const float* g, const float* in, const float* v, const float* h, float* gv, float* gh,
-                               int64_t B, int C, int c0, int H, int W, int accumulate, cudaStream_t s);
-
 #if SSTEM_BWD_PART == 0
 int launch_sepconv_bwd_taps_k51(const float* g, const float* in, const float* v, const float* h,
                                 float* gv, float* gh, int64_t B, int64_t C, int64_t H, int64_t W, bool gray, cudaStream_t s) {

@@ -328,5 +328,232 @@ sepconv_bwd_taps_k51_v3_kernel(const __grid_constant__ CUtensorMap map_in, const
     }
 }
 
+// =====================================================================================================================
+// Forward, same machinery: a warp owns 8 columns x 8 rows, walks 58 input rows (15 groups of 4) per tile.
+//   out[c][p] += v[fy = s - p][p] * sum_t P_c[s][x + g + 4t] * h[4t + g][p]
+// Per step: 13 LDS.128 (window), 8 LDS (vertical taps: plane s - p lives in this group's slot or one of the two before
+// it), 168 FFMA2.  Ring: 2 window slots, 4 vertical-tap slots, 2 barriers (group parity); the next tile's horizontal
+// taps (box {8 columns, 8 rows, 51 taps} = 13 KB) are prefetched while this tile computes.  The four tap groups of a
+// pixel are summed once per tile (transpose-reduce), after which lane g holds rows 2g, 2g+1.
+// =====================================================================================================================
+constexpr int F3_R = 8;
+constexpr int F3_ROWS = F3_R + K51 - 1;                          // 58
+constexpr unsigned F3_V_BYTES = V3_GROUP * F3_R * V3_COLS * 4;   // 1024: [plane][row][col]
+constexpr unsigned F3_H_BYTES = K51 * F3_R * V3_COLS * 4;        // 13056
+constexpr unsigned F3_OFF_V = 2 * V3_WIN_BYTES;                  // 7680
+constexpr unsigned F3_OFF_H = F3_OFF_V + 4 * F3_V_BYTES;         // 11776
+constexpr unsigned F3_OFF_BAR = F3_OFF_H + F3_H_BYTES;           // 24832
+constexpr unsigned F3_WARP_BYTES = F3_OFF_BAR + 128;             // 24960 = 195 * 128
+constexpr size_t F3_SMEM = (size_t)V3_WARPS * F3_WARP_BYTES + 128;
+
+template <int S>
+__device__ __forceinline__ void fwd3_step(unsigned pa, const unsigned (&va)[8], bool novalid,
+                                          const float2 (&h2)[4][13], float2 (&acc)[3][4]) {
+    constexpr int NP = 4, NT = 13;
+    float2 v2[NP];
+#pragma unroll
+    for (int pp = 0; pp < NP; ++pp) {                      // S >= 0: rows whose fy = S - p is outside 0..50 get v = 0
+        const bool a_ok = (S < 0) || (S - 2 * pp >= 0 && S - 2 * pp < K51);
+        const bool b_ok = (S < 0) || (S - 2 * pp - 1 >= 0 && S - 2 * pp - 1 < K51);
+        v2[pp].x = a_ok ? lds_f32(va[2 * pp]) : 0.f;
+        v2[pp].y = b_ok ? lds_f32(va[2 * pp + 1]) : 0.f;
+    }
+    float2 part[3][NP];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+        float4 P = lds_f32x4(pa + 64 * t);
+        if (t == NT - 1) {                                 // tap 51 does not exist (lanes g == 3)
+            P.x = novalid ? 0.f : P.x;
+            P.y = novalid ? 0.f : P.y;
+            P.z = novalid ? 0.f : P.z;
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float p = c == 0 ? P.x : (c == 1 ? P.y : P.z);
+#pragma unroll
+            for (int pp = 0; pp < NP; ++pp) {
+                if (S >= 0 && (S < 2 * pp || S > 2 * pp + K51)) continue;   // pair entirely outside
+                part[c][pp] = __ffma2_rn(make_float2(p, p), h2[pp][t], t == 0 ? make_float2(0.f, 0.f) : part[c][pp]);
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int pp = 0; pp < NP; ++pp) {
+            if (S >= 0) {
+                if (S < 2 * pp || S > 2 * pp + K51) continue;
+                // a row whose fy is out of range must not even see part (NaN / Inf safety)
+                if (S - 2 * pp > K51 - 1) part[c][pp].x = 0.f;
+                if (S - 2 * pp - 1 < 0) part[c][pp].y = 0.f;
+            }
+            acc[c][pp] = __ffma2_rn(v2[pp], part[c][pp], acc[c][pp]);
+        }
+}
+
+__global__ void __launch_bounds__(V3_WARPS * 32, 2)
+sepconv_fwd_k51_v3_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_v,
+                          const __grid_constant__ CUtensorMap map_h, float* __restrict__ out,
+                          int* __restrict__ next_tile_counter, const V3Shape sh) {
+    constexpr int G = 4, R = F3_R, NP = 4, NT = 13;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    const int pg = lane / G, g = lane % G;
+    const bool novalid = (g == 3);
+    const bool lead = (lane == 0);
+    const int nwarps = gridDim.x * V3_WARPS;
+    int tile = blockIdx.x * V3_WARPS + warp;
+    if (tile >= sh.ntiles) return;
+    int ntile = tile + nwarps;
+
+    const unsigned base = ((unsigned)__cvta_generic_to_shared(smem_raw) + 127u & ~127u) + warp * F3_WARP_BYTES;
+    const unsigned bar0 = base + F3_OFF_BAR;               // full[group parity] at +0 / +8, hbar at +16
+    const unsigned hbar = bar0 + 16;
+    if (lead) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8 * i), "r"(1));
+        mbar_fence_init();
+    }
+    __syncwarp();
+
+    const int64_t plane = (int64_t)sh.H * sh.W;
+    auto decode = [&](int t, int& b, int& y0, int& x0) {
+        const int tx = t % sh.tiles_x, r = t / sh.tiles_x;
+        x0 = tx * V3_COLS;
+        y0 = (r % sh.tiles_y) * R;
+        b = r / sh.tiles_y;
+    };
+    // window slots / barriers alternate (a = this group, b = next group); vertical-tap slots rotate through four
+    unsigned w_a = base, w_b = base + V3_WIN_BYTES, b_a = bar0, b_b = bar0 + 8, p_a = 0, p_b = 0, p_h = 0;
+    unsigned v_c = base + F3_OFF_V, v_n = v_c + F3_V_BYTES, v_f = v_c + 2 * F3_V_BYTES, v_p = v_c + 3 * F3_V_BYTES;
+    // v_c: this group, v_n: next group (in flight), v_f: free -> receives group + 2 at the end of this group... see end_group
+    auto issue_group = [&](unsigned wslot, unsigned vslot, unsigned bar, int b, int y0, int x0, int gi) {
+        if (lead) {
+            mbar_expect_tx_a(bar, V3_WIN_BYTES + F3_V_BYTES);
+            tma_load_3d_a(wslot, &map_in, bar, 4 * x0, y0 + V3_GROUP * gi, b);
+            tma_load_4d_a(vslot, &map_v, bar, x0, y0, V3_GROUP * gi, b);
+        }
+    };
+    auto issue_h = [&](int b, int y0, int x0) {
+        if (lead) {
+            mbar_expect_tx_a(hbar, F3_H_BYTES);
+            tma_load_4d_a(base + F3_OFF_H, &map_h, hbar, x0, y0, 0, b);
+        }
+    };
+
+    int tb, ty0, tx0;
+    decode(tile, tb, ty0, tx0);
+    issue_h(tb, ty0, tx0);
+    // vertical-tap slots in use at group i: v_c = i, v_p1 = i-1, v_p2 = i-2; v_n = i+1 in flight.  Four registers:
+    unsigned v_p1 = v_p, v_p2 = v_f;                       // contents irrelevant before the first groups (never read)
+    issue_group(w_a, v_c, b_a, tb, ty0, tx0, 0);
+    issue_group(w_b, v_n, b_b, tb, ty0, tx0, 1);
+
+    const unsigned lane_win = (unsigned)(pg + g) * 16u;
+    const unsigned lane_v = (unsigned)pg * 4u;
+
+#pragma unroll 1
+    for (;;) {
+        const bool has_next = ntile < sh.ntiles;
+        int nb = 0, ny0 = 0, nx0 = 0;
+        if (has_next) decode(ntile, nb, ny0, nx0);
+        int ticket = 0;
+        if (has_next && lead) ticket = atomicAdd(next_tile_counter, 1);
+
+        float2 h2[NP][NT], acc[3][NP];
+        mbar_wait_a(hbar, p_h);
+        p_h ^= 1;
+        {
+            const unsigned ha = base + F3_OFF_H + (unsigned)pg * 4u;
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                const int tap = (t == NT - 1 && novalid) ? (G * (NT - 2) + g) : (G * t + g);
+#pragma unroll
+                for (int pp = 0; pp < NP; ++pp)
+                    h2[pp][t] = make_float2(lds_f32(ha + ((tap * R + 2 * pp) * V3_COLS) * 4), lds_f32(ha + ((tap * R + 2 * pp + 1) * V3_COLS) * 4));
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int pp = 0; pp < NP; ++pp) acc[c][pp] = make_float2(0.f, 0.f);
+        __syncwarp();
+        if (has_next) issue_h(nb, ny0, nx0);
+
+        auto run_step = [&](auto gi_tag, auto u_tag, unsigned wa, unsigned vc, unsigned vp1, unsigned vp2) {
+            constexpr int GI = decltype(gi_tag)::value, U = decltype(u_tag)::value;
+            constexpr int S = GI < 0 ? -1 : GI * V3_GROUP + U;
+            if (GI >= 0 && GI * V3_GROUP + U >= F3_ROWS) return;          // rows 58, 59 of the last group
+            unsigned va[8];
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {                  // plane s - p: this group's slot or one of the two before
+                const int d = U - p;                       // -7 .. 3
+                const unsigned slot = d >= 0 ? vc : (d >= -4 ? vp1 : vp2);
+                const int pl = d >= 0 ? d : (d >= -4 ? d + 4 : d + 8);
+                va[p] = slot + (pl * R + p) * V3_COLS * 4;
+            }
+            fwd3_step<S>(wa + U * V3_WIN_COLS * 16, va, novalid, h2, acc);
+        };
+        auto run_group = [&](auto gi_tag) {
+            mbar_wait_a(b_a, p_a);
+            p_a ^= 1;
+            const unsigned wa = w_a + lane_win, vc = v_c + lane_v, vp1 = v_p1 + lane_v, vp2 = v_p2 + lane_v;
+            run_step(gi_tag, std::integral_constant<int, 0>{}, wa, vc, vp1, vp2);
+            run_step(gi_tag, std::integral_constant<int, 1>{}, wa, vc, vp1, vp2);
+            run_step(gi_tag, std::integral_constant<int, 2>{}, wa, vc, vp1, vp2);
+            run_step(gi_tag, std::integral_constant<int, 3>{}, wa, vc, vp1, vp2);
+        };
+        // end of group i: its window slot and the vertical-tap slot of group i-2 are free -> they receive group i+2
+        auto end_group = [&](bool next_tile, int gi_issue) {
+            __syncwarp();
+            if (next_tile) { if (has_next) issue_group(w_a, v_p2, b_a, nb, ny0, nx0, gi_issue); }
+            else issue_group(w_a, v_p2, b_a, tb, ty0, tx0, gi_issue);
+            unsigned t;
+            t = w_a; w_a = w_b; w_b = t;
+            t = b_a; b_a = b_b; b_b = t;
+            t = p_a; p_a = p_b; p_b = t;
+            t = v_p2; v_p2 = v_p1; v_p1 = v_c; v_c = v_n; v_n = t;   // (c, n, p1, p2) <- (n, old p2 [now filling], c, p1)
+        };
+
+        run_group(std::integral_constant<int, 0>{});
+        end_group(false, 2);
+        run_group(std::integral_constant<int, 1>{});
+        end_group(false, 3);
+#pragma unroll 1
+        for (int gi = 2; gi < 12; ++gi) {                  // groups 2..11 = steps 8..47: every row active
+            run_group(std::integral_constant<int, -1>{});
+            end_group(false, gi + 2);
+        }
+        run_group(std::integral_constant<int, 12>{});      // steps 48..51
+        end_group(false, 14);
+        run_group(std::integral_constant<int, 13>{});      // steps 52..55
+        end_group(true, 0);
+        run_group(std::integral_constant<int, 14>{});      // steps 56, 57
+        end_group(true, 1);
+
+        // ---- sum the 4 tap groups of each pixel: lane g ends up with rows 2g, 2g+1 of every channel
+        const int x = tx0 + pg;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float val[R];
+#pragma unroll
+            for (int pp = 0; pp < NP; ++pp) { val[2 * pp] = acc[c][pp].x; val[2 * pp + 1] = acc[c][pp].y; }
+            group_reduce<G, R>(val, g);
+            if (x < sh.W) {
+                float* ob = out + (((int64_t)tb * sh.C + sh.c0 + c) * sh.H + ty0) * sh.W + x;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int p = 2 * g + j;
+                    if (ty0 + p < sh.H) ob[(int64_t)p * sh.W] = val[j];
+                }
+            }
+        }
+        if (!has_next) break;
+        tile = ntile; tb = nb; ty0 = ny0; tx0 = nx0;
+        ntile = 2 * nwarps + __shfl_sync(0xffffffffu, ticket, 0);
+    }
+}
+
 }  // namespace
 }  // namespace sstem
