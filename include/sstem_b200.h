@@ -228,6 +228,8 @@ int sstem_sff_contrast(uint8_t* img, const int64_t* stats, const double* params,
  *   section_prev, section_next  [batch, h, w] uint8
  *   inputs                      [batch, 6, h + 2*pad, w + 2*pad] float32
  * Bit-equal to the numpy expression; only the uint8 sections have to cross PCIe.
+ * section_next == NULL: one section only -> inputs [batch, 3, h + 2*pad, w + 2*pad] (the correction module's
+ * input_sff, sff_scripts_fusion/inference.py:127-131,145).
  */
 int sstem_sections_to_input(const uint8_t* section_prev, const uint8_t* section_next, float* inputs,
                             int64_t batch, int64_t h, int64_t w, int32_t pad, void* stream);
@@ -242,6 +244,14 @@ int sstem_sections_to_input(const uint8_t* section_prev, const uint8_t* section_
  */
 int sstem_prediction_to_u8(const float* pred, uint8_t* section, int64_t batch, int64_t h, int64_t w,
                            int32_t pad, void* stream);
+
+/* Output assembly of the correction module -- replaces sff_scripts_fusion/inference.py:163-171:
+ *   warped_sff = (warped * 255).astype(np.uint8) -> PIL convert('L');  mask = warped_sff >= 2;
+ *   stitch = (img_interp * (1 - mask) + warped_sff * mask).astype(np.uint8)
+ * warped: float32 [B,C,H,W] (C = 1 or 3: the SpatialTransformation output), interp: uint8 [B,H,W] (the interpolated
+ * section), gray_out (nullable) / stitch_out: uint8 [B,H,W].  H*W must be a multiple of 4.  Bit-equal to numpy + PIL. */
+int sstem_warp_stitch_u8(const float* warped, const uint8_t* interp, uint8_t* gray_out, uint8_t* stitch_out,
+                         int64_t B, int64_t C, int64_t H, int64_t W, void* stream);
 
 /*
  * FP32 FMA-pipe probe: runs a register-resident FFMA loop on every SM of the

@@ -389,3 +389,26 @@ def prediction_to_uint8_restated(pred, pad):
     if pad:
         pred = pred[..., pad:-pad, pad:-pad]
     return (np.squeeze(pred) * 255).astype(np.uint8)
+
+
+def warp_stitch_restated(warped, img_interp):
+    """sff_scripts_fusion/inference.py:163-171 restated in numpy (test oracle):
+
+        warped_sff = (np.squeeze(warped) * 255).astype(np.uint8)             # [C,H,W]
+        warped_sff = np.asarray(Image.fromarray(warped_sff.transpose(1,2,0)).convert('L'))
+        mask = np.ones_like(warped_sff, np.float32); mask[warped_sff < 2] = 0
+        stitch = (img_interp * (1 - mask) + warped_sff * mask).astype(np.uint8)
+
+    ``warped``: float32 [C,H,W] (C = 1 or 3), ``img_interp``: uint8 [H,W].  Pillow's RGB -> 'L' is the fixed-point ITU-R
+    601 luma ``(19595 R + 38470 G + 7471 B + 0x8000) >> 16`` (Pillow src/libImaging/Convert.c, macro L24); a CPU test pins
+    this restatement against Pillow itself.  Returns (warped_gray uint8 [H,W], stitch uint8 [H,W])."""
+    w8 = (np.asarray(warped, np.float32) * np.float32(255)).astype(np.uint8)
+    if w8.shape[0] == 3:
+        r, g, b = (w8[i].astype(np.uint32) for i in range(3))
+        gray = ((19595 * r + 38470 * g + 7471 * b + 0x8000) >> 16).astype(np.uint8)
+    else:
+        gray = w8[0]
+    mask = np.ones_like(gray, dtype=np.float32)
+    mask[gray < 2] = 0
+    stitch = (img_interp * (1 - mask) + gray * mask).astype(np.uint8)
+    return gray, stitch

@@ -37,7 +37,7 @@ WARP_NEAREST = 1
 EXPORTED_SYMBOLS = (
     "sstem_sepconv_forward", "sstem_sepconv_backward", "sstem_interp_tail_forward", "sstem_interp_tail_backward",
     "sstem_warp_forward", "sstem_image_warp", "sstem_sff_degrade", "sstem_sff_contrast",
-    "sstem_sections_to_input", "sstem_prediction_to_u8",
+    "sstem_sections_to_input", "sstem_prediction_to_u8", "sstem_warp_stitch_u8",
     "sstem_fp32_peak_probe", "sstem_launch_count", "sstem_abi_version", "sstem_error_string",
 )
 
@@ -82,6 +82,8 @@ def load() -> ctypes.CDLL:
         lib.sstem_sections_to_input.restype = ctypes.c_int
         lib.sstem_prediction_to_u8.argtypes = [_c_p] * 2 + [_c_i64] * 3 + [_c_i32, _c_p]
         lib.sstem_prediction_to_u8.restype = ctypes.c_int
+        lib.sstem_warp_stitch_u8.argtypes = [_c_p] * 4 + [_c_i64] * 4 + [_c_p]
+        lib.sstem_warp_stitch_u8.restype = ctypes.c_int
         lib.sstem_fp32_peak_probe.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
         lib.sstem_fp32_peak_probe.restype = ctypes.c_int
         lib.sstem_launch_count.argtypes = []

@@ -122,6 +122,9 @@ int try_launch_bwd_taps_k51_v3(const float* g, const float* in, const float* v, 
     if ((W & 3) || !aligned16(v) || !aligned16(h) || !aligned16(g) || ((int64_t)H * W * c0 & 3)) return -1000;
     const int64_t tiles_x = (W + V3_COLS - 1) / V3_COLS, tiles_y = (H + V2_R - 1) / V2_R;
     if (tiles_x * tiles_y * B > INT32_MAX / 2) return -1000;
+    // a persistent grid needs several tiles per warp to balance; small problems stay on the CTA-per-tile kernel
+    static const int64_t min_tiles = getenv("SSTEM_V3_MIN_TILES") ? atoll(getenv("SSTEM_V3_MIN_TILES")) : 6;    // measured crossover: ~6 tiles per warp (tap gradients), ~10 (forward)
+    if (tiles_x * tiles_y * B < min_tiles * 2 * sm_count() * V3_WARPS) return -1000;
     const int64_t IH = H + K51 - 1, IW = W + K51 - 1;
     float* ws = nullptr;
     const size_t ws_bytes = (size_t)(B * IH * IW) * 16;
@@ -155,7 +158,7 @@ int try_launch_bwd_taps_k51_v2(const float* g, const float* in, const float* v, 
         const int e3 = try_launch_bwd_taps_k51_v3(g, in, v, h, gv, gh, B, C, c0, H, W, accumulate, s);
         if (e3 != -1000) return e3;
     }
-    const bool off = gen < 2;
+    const bool off = gen != 2;                             // generation 2 is kept for A/B runs only (SSTEM_BWD_GEN=2)
     if (off || (W & 3) || !aligned16(v) || B > 65535 || (H + V2_R - 1) / V2_R > 65535) return -1000;
     const int64_t IH = H + K51 - 1, IW = W + K51 - 1;
     float* ws = nullptr;

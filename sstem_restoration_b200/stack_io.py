@@ -29,26 +29,32 @@ def _cuda(t, dtype):
     return t.contiguous(), host
 
 
-def sections_to_input(section_prev, section_next, pad=0):
-    """uint8 ``[H,W]`` or ``[B,H,W]`` sections k-1 and k+1 -> float32 ``[B,6,H+2*pad,W+2*pad]`` on the device."""
+def sections_to_input(section_prev, section_next=None, pad=0):
+    """uint8 ``[H,W]`` or ``[B,H,W]`` sections k-1 and k+1 -> float32 ``[B,6,H+2*pad,W+2*pad]`` on the device.
+    ``section_next=None``: one section -> ``[B,3,H+2*pad,W+2*pad]`` (gray x3, /255: the correction module's
+    ``input_sff``, sff_scripts_fusion/inference.py:127-131)."""
     a, _ = _cuda(section_prev, torch.uint8)
-    b, _ = _cuda(section_next, torch.uint8)
+    b = None
+    if section_next is not None:
+        b, _ = _cuda(section_next, torch.uint8)
     if a.dim() == 2:
-        a, b = a[None], b[None]
-    if a.dim() != 3 or a.shape != b.shape or a.device != b.device:
+        a = a[None]
+        b = b[None] if b is not None else None
+    if a.dim() != 3 or (b is not None and (a.shape != b.shape or a.device != b.device)):
         raise ValueError("sections_to_input: two uint8 sections of the same shape [H,W] or [B,H,W]")
     B, H, W = a.shape
-    out = torch.empty((B, 6, H + 2 * pad, W + 2 * pad), dtype=torch.float32, device=a.device)
+    out = torch.empty((B, 6 if b is not None else 3, H + 2 * pad, W + 2 * pad), dtype=torch.float32, device=a.device)
     if out.numel():
-        code = _lib.load().sstem_sections_to_input(a.data_ptr(), b.data_ptr(), out.data_ptr(), B, H, W, pad,
+        code = _lib.load().sstem_sections_to_input(a.data_ptr(), b.data_ptr() if b is not None else None, out.data_ptr(), B, H, W, pad,
                                                    torch.cuda.current_stream(a.device).cuda_stream)
         if code:
             _lib.check(code, "sstem_sections_to_input")
     return out
 
 
-def prediction_to_uint8(pred, pad=0):
-    """float32 ``[B,1,H+2*pad,W+2*pad]`` (or ``[H+2*pad,W+2*pad]``) -> uint8 ``[B,H,W]`` (``[H,W]``)."""
+def prediction_to_uint8(pred, pad=0, out=None):
+    """float32 ``[B,1,H+2*pad,W+2*pad]`` (or ``[H+2*pad,W+2*pad]``) -> uint8 ``[B,H,W]`` (``[H,W]``).
+    ``out``: optional contiguous uint8 CUDA tensor ``[B,H,W]`` to write into (e.g. a slice of a stack)."""
     p, host = _cuda(pred, torch.float32)
     squeeze = p.dim() == 2
     if squeeze:
@@ -59,7 +65,10 @@ def prediction_to_uint8(pred, pad=0):
     H, W = OH - 2 * pad, OW - 2 * pad
     if H <= 0 or W <= 0:
         raise ValueError("prediction_to_uint8: pad larger than the prediction")
-    out = torch.empty((B, H, W), dtype=torch.uint8, device=p.device)
+    if out is None:
+        out = torch.empty((B, H, W), dtype=torch.uint8, device=p.device)
+    elif not (out.is_cuda and out.dtype == torch.uint8 and out.is_contiguous() and tuple(out.shape) == (B, H, W) and out.device == p.device):
+        raise ValueError("prediction_to_uint8: out must be a contiguous uint8 CUDA tensor [B,H,W] on pred's device")
     code = _lib.load().sstem_prediction_to_u8(p.data_ptr(), out.data_ptr(), B, H, W, pad,
                                               torch.cuda.current_stream(p.device).cuda_stream)
     if code:

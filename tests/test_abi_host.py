@@ -159,7 +159,10 @@ def test_argument_errors_of_the_section_8f_entry_points(built_lib):
     assert lib.sstem_sff_degrade(p, p, p, None, None, None, p, 1, 4, 4, 2, None) == -2           # border swallows the image
     assert lib.sstem_sff_degrade(p, p + 4, p, None, None, None, p, 1, 4, 4, 0, None) == -3       # params not 8-byte aligned
     assert lib.sstem_sff_contrast(p, p, p, 1, 4, 4, 0, 4, None) == -2
-    assert lib.sstem_sections_to_input(p, None, p, 1, 4, 4, 0, None) == -1
+    assert lib.sstem_sections_to_input(None, p, p, 1, 4, 4, 0, None) == -1                        # (section_next may be NULL)
+    assert lib.sstem_warp_stitch_u8(p, None, p, p, 1, 3, 4, 4, None) == -1
+    assert lib.sstem_warp_stitch_u8(p, p, None, p, 1, 2, 4, 4, None) == -2                        # 1 or 3 channels
+    assert lib.sstem_warp_stitch_u8(p, p, None, p, 1, 3, 3, 3, None) == -2                        # H*W % 4
     assert lib.sstem_sections_to_input(p, p, p, 1, 4, 4, -1, None) == -2
     assert lib.sstem_prediction_to_u8(p, None, 1, 4, 4, 0, None) == -1
     assert lib.sstem_prediction_to_u8(p + 1, p, 1, 4, 4, 0, None) == -3

@@ -60,3 +60,59 @@ def test_type_errors():
         pkg.sections_to_input(torch.zeros((4, 4), device="cuda"), torch.zeros((4, 4), device="cuda"))
     with pytest.raises(TypeError):
         pkg.prediction_to_uint8(torch.zeros((4, 4), dtype=torch.uint8, device="cuda"))
+
+
+@pytest.mark.parametrize("C,H,W", [(3, 36, 44), (1, 36, 44), (3, 256, 256)])
+def test_warp_stitch_bit_exact(C, H, W):
+    """sff_scripts_fusion/inference.py:163-171 (uint8 cast, PIL 'L', stitch mask) on the device."""
+    r = np.random.default_rng(C * H)
+    w = r.random((2, C, H, W), dtype=np.float32)
+    w[:, :, 5:9, :] = 0.004                                    # below 2/255: taken from the interpolated section
+    w[0, :, 20, 3] = 1.0
+    interp = r.integers(0, 256, (2, H, W), dtype=np.uint8)
+    gray, stitch = pkg.warp_stitch(torch.from_numpy(w).cuda(), torch.from_numpy(interp).cuda())
+    for b in range(2):
+        want_gray, want_stitch = oracle.warp_stitch_restated(w[b], interp[b])
+        assert np.array_equal(gray[b].cpu().numpy(), want_gray)
+        assert np.array_equal(stitch[b].cpu().numpy(), want_stitch)
+
+
+def test_sections_to_input_single_section():
+    r = np.random.default_rng(9)
+    a = r.integers(0, 256, (40, 48), dtype=np.uint8)
+    got = pkg.sections_to_input(torch.from_numpy(a).cuda(), None, 3)
+    want = oracle.sections_to_input_restated(a, a, 3)[:, :3]
+    assert got.shape == (1, 3, 46, 54) and np.array_equal(got.cpu().numpy().view(np.uint32), want.view(np.uint32))
+
+
+def test_restore_stack_matches_the_op_by_op_expression():
+    """restore_stack (uint8 wire, prefetching uploads, fused tail, warp, stitch) == the same steps spelled out with the
+    oracle-checked operators one target at a time, bit for bit; also from a CUDA-resident stack and with to_host."""
+    N, H, W = 6, 64, 96
+    stack = torch.from_numpy(np.stack([synth.em_section(H, W, 20 + i) for i in range(N)]))
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    taps = [torch.softmax(torch.randn((1, 51, H, W), device="cuda", generator=gen), 1) for _ in range(4)]
+    flow_np, _ = synth.random_fold_flow(H, W, 555)
+    flow = torch.from_numpy(np.ascontiguousarray(flow_np.transpose(2, 0, 1))[None]).cuda().permute(0, 2, 3, 1)
+    seen = []
+
+    def taps_fn(k, x):
+        seen.append(k)
+        assert x.shape == (1, 6, H, W)
+        return taps
+
+    res = pkg.restore_stack(stack.pin_memory(), taps_fn, lambda k, xk, interp: flow, to_host=True)
+    assert seen == [1, 2, 3, 4] and res["stats"]["targets"] == 4 and res["stats"]["h2d_bytes"] == N * H * W
+    warp = pkg.SpatialTransformation(True)
+    for i, k in enumerate(range(1, N - 1)):
+        x = pkg.sections_to_input(stack[k - 1].cuda(), stack[k + 1].cuda(), 0)
+        interp = pkg.prediction_to_uint8(pkg.interpolation_tail(x[:, :3], x[:, 3:6], *taps), 0)
+        warped = warp(pkg.sections_to_input(stack[k].cuda(), None, 0), flow)
+        gray, stitch = oracle.warp_stitch_restated(warped[0].cpu().numpy(), interp[0].cpu().numpy())
+        assert torch.equal(res["interp"][i], interp[0].cpu())
+        assert np.array_equal(res["warped"][i].numpy(), gray) and np.array_equal(res["stitch"][i].numpy(), stitch)
+    on_dev = pkg.restore_stack(stack.cuda(), taps_fn, None)
+    assert set(on_dev) == {"interp", "stats"} and torch.equal(on_dev["interp"].cpu(), res["interp"])
+    # the per-rank shards of a 3-way split (no process group here: each call returns its own shard) tile the result
+    parts = [pkg.restore_stack(stack.cuda(), taps_fn, None, rank=r, world_size=3)["interp"] for r in range(3)]
+    assert [p.shape[0] for p in parts] == [2, 1, 1] and torch.equal(torch.cat(parts), on_dev["interp"])

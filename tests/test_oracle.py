@@ -222,3 +222,25 @@ def test_kpn_taps_fixture_and_compat_import_path(golden_dir):
     ref64 = oracle.sepconv_forward_f64(inp, taps["k2v"], taps["k2h"])
     scale = max(1.0, float(np.abs(ref64).max()))
     assert float(np.abs(ref32 - ref64).max()) <= 1e-5 * scale
+
+
+def test_warp_stitch_restatement_matches_pillow():
+    """sff_scripts_fusion/inference.py:163-171 converts the warped RGB section with PIL's 'L' mode: pin the fixed-point
+    luma formula of the restatement against Pillow itself (gray x3 and genuinely coloured triples)."""
+    Image = pytest.importorskip("PIL.Image")
+    r = np.random.default_rng(7)
+    for kind in ("gray", "rgb"):
+        w = r.random((3, 37, 41), dtype=np.float32)
+        if kind == "gray":
+            w[1:] = w[:1]
+        w[:, 3:9, 5:20] = 0.003                                # warped_sff < 2: the fold line, filled from the interpolation
+        interp = r.integers(0, 256, (37, 41), dtype=np.uint8)
+        w8 = (w * 255).astype(np.uint8)
+        pil = np.asarray(Image.fromarray(np.transpose(w8, (1, 2, 0))).convert("L"))
+        mask = np.ones_like(pil, dtype=np.float32)
+        mask[pil < 2] = 0
+        want = (interp * (1 - mask) + pil * mask).astype(np.uint8)
+        gray, stitch = oracle.warp_stitch_restated(w, interp)
+        assert np.array_equal(gray, pil) and np.array_equal(stitch, want)
+        if kind == "gray":
+            assert np.array_equal(gray, w8[0])
