@@ -80,7 +80,7 @@ int launch_v3_kernel(const CUtensorMap& min, const CUtensorMap& mv, const CUtens
     static PerDeviceOnce done;
     auto kern = sepconv_bwd_taps_k51_v3_kernel<WV, WH, ACCUM>;
     if (int e = set_smem_once(kern, V3_SMEM, done)) return e;
-    const int ctas = std::min<int64_t>(2 * (int64_t)sm_count(), ((int64_t)sh.ntiles + V3_WARPS - 1) / V3_WARPS);
+    const int ctas = std::min<int64_t>(2 * (int64_t)sm_count(), (int64_t)sh.ntiles);
     kern<<<ctas, V3_WARPS * 32, V3_SMEM, s>>>(min, mv, mh, mg, gv, gh, counter, sh);
     count_launch();
     return finish_launch();
@@ -120,11 +120,11 @@ bool make_v3_maps(CUtensorMap* min, CUtensorMap* mv, CUtensorMap* mh, CUtensorMa
 int try_launch_bwd_taps_k51_v3(const float* g, const float* in, const float* v, const float* h, float* gv, float* gh,
                                int64_t B, int C, int c0, int H, int W, int accumulate, cudaStream_t s) {
     if ((W & 3) || !aligned16(v) || !aligned16(h) || !aligned16(g) || ((int64_t)H * W * c0 & 3)) return -1000;
-    const int64_t tiles_x = (W + V3_COLS - 1) / V3_COLS, tiles_y = (H + V2_R - 1) / V2_R;
+    const int64_t tiles_x = (W + V3_COLS * V3_WARPS - 1) / (V3_COLS * V3_WARPS), tiles_y = (H + V2_R - 1) / V2_R;
     if (tiles_x * tiles_y * B > INT32_MAX / 2) return -1000;
     // a persistent grid needs several tiles per warp to balance; small problems stay on the CTA-per-tile kernel
     static const int64_t min_tiles = getenv("SSTEM_V3_MIN_TILES") ? atoll(getenv("SSTEM_V3_MIN_TILES")) : 6;    // measured crossover: ~6 tiles per warp (tap gradients), ~10 (forward)
-    if (tiles_x * tiles_y * B < min_tiles * 2 * sm_count() * V3_WARPS) return -1000;
+    if (tiles_x * tiles_y * B < min_tiles * 2 * sm_count()) return -1000;
     const int64_t IH = H + K51 - 1, IW = W + K51 - 1;
     float* ws = nullptr;
     const size_t ws_bytes = (size_t)(B * IH * IW) * 16;

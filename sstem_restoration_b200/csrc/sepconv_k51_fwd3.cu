@@ -11,11 +11,11 @@ int try_launch_fwd_k51_v3(const float* in, const float* v, const float* h, float
                           int64_t B, int C, int c0, int H, int W, cudaStream_t s) {
     static const int gen = getenv("SSTEM_FWD_GEN") ? atoi(getenv("SSTEM_FWD_GEN")) : 3;   // experiments: force generation 1
     if (gen < 3 || (W & 3) || !aligned16(v) || !aligned16(h)) return -1000;
-    const int64_t tiles_x = (W + V3_COLS - 1) / V3_COLS, tiles_y = (H + F3_R - 1) / F3_R;
+    const int64_t tiles_x = (W + V3_COLS * V3_WARPS - 1) / (V3_COLS * V3_WARPS), tiles_y = (H + F3_R - 1) / F3_R;
     if (tiles_x * tiles_y * B > INT32_MAX / 2) return -1000;
     // a persistent grid needs several tiles per warp to balance; small problems stay on the CTA-per-tile kernel
     static const int64_t min_tiles = getenv("SSTEM_V3_MIN_TILES") ? atoll(getenv("SSTEM_V3_MIN_TILES")) : 10;   // measured crossover: ~10 tiles per warp (forward), ~6 (tap gradients)
-    if (tiles_x * tiles_y * B < min_tiles * 2 * sm_count() * V3_WARPS) return -1000;
+    if (tiles_x * tiles_y * B < min_tiles * 2 * sm_count()) return -1000;
     const int64_t IH = H + K51 - 1, IW = W + K51 - 1, plane = (int64_t)H * W;
     float* ws = nullptr;
     const size_t ws_bytes = (size_t)(B * IH * IW) * 16;
@@ -39,7 +39,7 @@ int try_launch_fwd_k51_v3(const float* in, const float* v, const float* h, float
         e = set_smem_once(kern, F3_SMEM, done);
         if (!e) {
             V3Shape sh{H, W, (int)tiles_x, (int)tiles_y, (int)(tiles_x * tiles_y * B), C, c0};
-            const int ctas = (int)std::min<int64_t>(2 * (int64_t)sm_count(), ((int64_t)sh.ntiles + V3_WARPS - 1) / V3_WARPS);
+            const int ctas = (int)std::min<int64_t>(2 * (int64_t)sm_count(), (int64_t)sh.ntiles);
             kern<<<ctas, V3_WARPS * 32, F3_SMEM, s>>>(min, mv, mh, out, counter, sh);
             count_launch();
             e = finish_launch();

@@ -58,15 +58,35 @@ __device__ __forceinline__ void mbar_wait_a(unsigned bar_addr, unsigned parity) 
         "bra WAIT_LOOP;\n\t"
         "DONE:\n\t}" ::"r"(bar_addr), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void tma_load_4d_a(unsigned dst, const CUtensorMap* map, unsigned bar, int c0, int c1, int c2, int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+// L2 policies: a window row is read by ~14 tile rows within a few tens of microseconds (evict last) and must not be
+// pushed out by the 1.7 GB of taps streaming past it.  The taps keep the normal policy: a warp tile reads 32 bytes of
+// each 64-byte DRAM sector and its neighbour the other half -- marked evict-first the sector was often gone before
+// the neighbour asked (measured: +0.5 GB of DRAM reads per launch).
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
 }
-__device__ __forceinline__ void tma_load_3d_a(unsigned dst, const CUtensorMap* map, unsigned bar, int c0, int c1, int c2) {
+__device__ __forceinline__ uint64_t l2_policy_evict_normal() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void tma_load_4d_a(unsigned dst, const CUtensorMap* map, unsigned bar, int c0, int c1, int c2, int c3,
+                                              uint64_t policy) {
     asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_a(unsigned dst, const CUtensorMap* map, unsigned bar, int c0, int c1, int c2, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(policy) : "memory");
 }
 __device__ __forceinline__ float lds_f32(unsigned addr) {
     float v;
@@ -153,14 +173,20 @@ sepconv_bwd_taps_k51_v3_kernel(const __grid_constant__ CUtensorMap map_in, const
     const int pg = lane / G, g = lane % G;
     const bool novalid = (g == 3);
     const bool lead = (lane == 0);
-    // Tiles are handed out dynamically (one atomic per warp and tile): warps do not run at the same speed (L2 distance,
-    // DRAM refresh, the other warp on the scheduler), and with a static round-robin the kernel waited for the slowest warp
-    // while 14 % of the warp slots sat empty (ncu: warps_active 6.9 of 8).  The first two tiles of a warp are static, so
-    // the prefetch of the next tile's taps never waits for an atomic: the ticket drawn at the start of tile k is tile k+2.
-    const int nwarps = gridDim.x * V3_WARPS;
-    int tile = blockIdx.x * V3_WARPS + warp;
+    // Tiles are handed out dynamically: SMs do not run at the same speed (L2 distance, DRAM refresh), and with a static
+    // round-robin the kernel waited for the slowest warp while 14 % of the warp slots sat empty (ncu: warps_active 6.9
+    // of 8).  The unit is a CTA tile = 4 adjacent warp tiles (32 columns): the four warps then request the same 128-byte
+    // lines of taps at the same time from the same SM -- with per-warp tickets neighbouring tiles ran up to a tile
+    // apart on different SMs and half-used lines were fetched twice (ncu: +0.6 GB of DRAM reads per launch).  One
+    // named barrier per tile keeps the four warps on the same ticket; inside a tile they never synchronise.  The first
+    // two tiles of a CTA are static, so the prefetch of the next tile's taps never waits for an atomic: the ticket drawn
+    // at the start of tile k is tile k+2.
+    __shared__ int s_ticket[2];
+    const int nctas = gridDim.x;
+    int tile = blockIdx.x;
     if (tile >= sh.ntiles) return;
-    int ntile = tile + nwarps;
+    int ntile = tile + nctas;
+    int tile_no = 0;
 
     const unsigned base = ((unsigned)__cvta_generic_to_shared(smem_raw) + 127u & ~127u) + warp * V3_WARP_BYTES;
     const unsigned bar0 = base + V3_OFF_BAR;               // full[slot] at bar0 + 8 * slot, hbar at bar0 + 24
@@ -172,11 +198,12 @@ sepconv_bwd_taps_k51_v3_kernel(const __grid_constant__ CUtensorMap map_in, const
         mbar_fence_init();
     }
     __syncwarp();
+    const uint64_t pol_once = l2_policy_evict_normal(), pol_keep = l2_policy_evict_last();
 
     const int64_t plane = (int64_t)sh.H * sh.W;
     auto decode = [&](int t, int& b, int& y0, int& x0) {
         const int tx = t % sh.tiles_x, r = t / sh.tiles_x;
-        x0 = tx * V3_COLS;
+        x0 = (tx * V3_WARPS + warp) * V3_COLS;
         y0 = (r % sh.tiles_y) * R;
         b = r / sh.tiles_y;
     };
@@ -187,15 +214,15 @@ sepconv_bwd_taps_k51_v3_kernel(const __grid_constant__ CUtensorMap map_in, const
     auto issue_group = [&](unsigned slot, unsigned bar, int b, int y0, int x0, int gi) {
         if (lead) {
             mbar_expect_tx_a(bar, V3_WIN_BYTES + (WH ? V3_V_BYTES : 0u));
-            tma_load_3d_a(slot, &map_in, bar, 4 * x0, y0 + V3_GROUP * gi, b);   // rows of 60 pixels x 4 floats: 960 contiguous bytes
-            if (WH) tma_load_4d_a(slot + V3_WIN_BYTES, &map_v, bar, x0, y0, V3_GROUP * gi, b);
+            tma_load_3d_a(slot, &map_in, bar, 4 * x0, y0 + V3_GROUP * gi, b, pol_keep);   // rows of 60 pixels x 4 floats: 960 contiguous bytes
+            if (WH) tma_load_4d_a(slot + V3_WIN_BYTES, &map_v, bar, x0, y0, V3_GROUP * gi, b, pol_once);
         }
     };
     auto issue_hg = [&](int b, int y0, int x0) {
         if (lead) {
             mbar_expect_tx_a(hbar, (WV ? V3_H_BYTES : 0u) + V3_G_BYTES);
-            if (WV) tma_load_4d_a(base + V3_OFF_H, &map_h, hbar, x0, y0, 0, b);
-            tma_load_4d_a(base + V3_OFF_G, &map_g, hbar, x0, y0, 0, b);
+            if (WV) tma_load_4d_a(base + V3_OFF_H, &map_h, hbar, x0, y0, 0, b, pol_once);
+            tma_load_4d_a(base + V3_OFF_G, &map_g, hbar, x0, y0, 0, b, pol_once);
         }
     };
     auto rotate = [&]() {                                  // (cur, nxt, prv) <- (nxt, prv, cur)
@@ -219,8 +246,7 @@ sepconv_bwd_taps_k51_v3_kernel(const __grid_constant__ CUtensorMap map_in, const
         const bool has_next = ntile < sh.ntiles;
         int nb = 0, ny0 = 0, nx0 = 0;
         if (has_next) decode(ntile, nb, ny0, nx0);
-        int ticket = 0;
-        if (has_next && lead) ticket = atomicAdd(next_tile_counter, 1);   // consumed at the end of this tile
+        if (has_next && warp == 0 && lead) s_ticket[tile_no & 1] = atomicAdd(next_tile_counter, 1);   // read after this tile's barrier
 
         // ---- this tile's horizontal taps and upstream gradient: shared memory -> registers
         float2 h2[NP][NT], gh2[NP][NT], g2[3][NP];
@@ -261,7 +287,7 @@ sepconv_bwd_taps_k51_v3_kernel(const __grid_constant__ CUtensorMap map_in, const
 #pragma unroll
                 for (int pp = 0; pp < NP; ++pp) { val[2 * pp] = gvp[pp].x; val[2 * pp + 1] = gvp[pp].y; }
                 group_reduce<G, R>(val, g);                // lane g now holds the total of row g
-                if (gv_row_ok && fy >= 0 && fy < K51) *gv_ptr = ACCUM ? (*gv_ptr + val[0]) : val[0];
+                if (gv_row_ok && fy >= 0 && fy < K51) __stcs(gv_ptr, ACCUM ? (*gv_ptr + val[0]) : val[0]);
                 gv_ptr += plane;
             }
         };
@@ -317,14 +343,16 @@ sepconv_bwd_taps_k51_v3_kernel(const __grid_constant__ CUtensorMap map_in, const
                     const int ya = ty0 + 2 * pp, yb = ya + 1;
                     float* da = gp + (int64_t)(G * t) * plane + (int64_t)ya * sh.W;
                     float* db = gp + (int64_t)(G * t) * plane + (int64_t)yb * sh.W;
-                    if (ya < sh.H) *da = ACCUM ? (*da + gh2[pp][t].x) : gh2[pp][t].x;
-                    if (yb < sh.H) *db = ACCUM ? (*db + gh2[pp][t].y) : gh2[pp][t].y;
+                    if (ya < sh.H) __stcs(da, ACCUM ? (*da + gh2[pp][t].x) : gh2[pp][t].x);
+                    if (yb < sh.H) __stcs(db, ACCUM ? (*db + gh2[pp][t].y) : gh2[pp][t].y);
                 }
             }
         }
         if (!has_next) break;
+        asm volatile("bar.sync 1, %0;" ::"n"(V3_WARPS * 32) : "memory");   // the CTA moves to its next tile together
         tile = ntile; tb = nb; ty0 = ny0; tx0 = nx0;
-        ntile = 2 * nwarps + __shfl_sync(0xffffffffu, ticket, 0);
+        ntile = 2 * nctas + *reinterpret_cast<volatile int*>(&s_ticket[tile_no & 1]);
+        ++tile_no;
     }
 }
 
@@ -401,10 +429,12 @@ sepconv_fwd_k51_v3_kernel(const __grid_constant__ CUtensorMap map_in, const __gr
     const int pg = lane / G, g = lane % G;
     const bool novalid = (g == 3);
     const bool lead = (lane == 0);
-    const int nwarps = gridDim.x * V3_WARPS;
-    int tile = blockIdx.x * V3_WARPS + warp;
+    __shared__ int s_ticket[2];                            // CTA-level dynamic tile tickets: see the tap-gradient kernel
+    const int nctas = gridDim.x;
+    int tile = blockIdx.x;
     if (tile >= sh.ntiles) return;
-    int ntile = tile + nwarps;
+    int ntile = tile + nctas;
+    int tile_no = 0;
 
     const unsigned base = ((unsigned)__cvta_generic_to_shared(smem_raw) + 127u & ~127u) + warp * F3_WARP_BYTES;
     const unsigned bar0 = base + F3_OFF_BAR;               // full[group parity] at +0 / +8, hbar at +16
@@ -416,11 +446,12 @@ sepconv_fwd_k51_v3_kernel(const __grid_constant__ CUtensorMap map_in, const __gr
         mbar_fence_init();
     }
     __syncwarp();
+    const uint64_t pol_once = l2_policy_evict_normal(), pol_keep = l2_policy_evict_last();
 
     const int64_t plane = (int64_t)sh.H * sh.W;
     auto decode = [&](int t, int& b, int& y0, int& x0) {
         const int tx = t % sh.tiles_x, r = t / sh.tiles_x;
-        x0 = tx * V3_COLS;
+        x0 = (tx * V3_WARPS + warp) * V3_COLS;
         y0 = (r % sh.tiles_y) * R;
         b = r / sh.tiles_y;
     };
@@ -431,14 +462,14 @@ sepconv_fwd_k51_v3_kernel(const __grid_constant__ CUtensorMap map_in, const __gr
     auto issue_group = [&](unsigned wslot, unsigned vslot, unsigned bar, int b, int y0, int x0, int gi) {
         if (lead) {
             mbar_expect_tx_a(bar, V3_WIN_BYTES + F3_V_BYTES);
-            tma_load_3d_a(wslot, &map_in, bar, 4 * x0, y0 + V3_GROUP * gi, b);
-            tma_load_4d_a(vslot, &map_v, bar, x0, y0, V3_GROUP * gi, b);
+            tma_load_3d_a(wslot, &map_in, bar, 4 * x0, y0 + V3_GROUP * gi, b, pol_keep);
+            tma_load_4d_a(vslot, &map_v, bar, x0, y0, V3_GROUP * gi, b, pol_once);
         }
     };
     auto issue_h = [&](int b, int y0, int x0) {
         if (lead) {
             mbar_expect_tx_a(hbar, F3_H_BYTES);
-            tma_load_4d_a(base + F3_OFF_H, &map_h, hbar, x0, y0, 0, b);
+            tma_load_4d_a(base + F3_OFF_H, &map_h, hbar, x0, y0, 0, b, pol_once);
         }
     };
 
@@ -458,8 +489,7 @@ sepconv_fwd_k51_v3_kernel(const __grid_constant__ CUtensorMap map_in, const __gr
         const bool has_next = ntile < sh.ntiles;
         int nb = 0, ny0 = 0, nx0 = 0;
         if (has_next) decode(ntile, nb, ny0, nx0);
-        int ticket = 0;
-        if (has_next && lead) ticket = atomicAdd(next_tile_counter, 1);
+        if (has_next && warp == 0 && lead) s_ticket[tile_no & 1] = atomicAdd(next_tile_counter, 1);
 
         float2 h2[NP][NT], acc[3][NP];
         mbar_wait_a(hbar, p_h);
@@ -550,8 +580,10 @@ sepconv_fwd_k51_v3_kernel(const __grid_constant__ CUtensorMap map_in, const __gr
             }
         }
         if (!has_next) break;
+        asm volatile("bar.sync 1, %0;" ::"n"(V3_WARPS * 32) : "memory");   // the CTA moves to its next tile together
         tile = ntile; tb = nb; ty0 = ny0; tx0 = nx0;
-        ntile = 2 * nwarps + __shfl_sync(0xffffffffu, ticket, 0);
+        ntile = 2 * nctas + *reinterpret_cast<volatile int*>(&s_ticket[tile_no & 1]);
+        ++tile_no;
     }
 }
 
