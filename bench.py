@@ -191,8 +191,10 @@ def _cpu_model():
 
 
 def _traffic():
-    """DRAM bytes per launch from the committed `ncu --set full` captures (profiles/traffic_r1.json)."""
-    path = os.path.join(ROOT, "profiles", "traffic_r1.json")
+    """DRAM bytes per launch from the committed ncu captures (profiles/traffic_r2.json; round 1's as fall-back)."""
+    path = os.path.join(ROOT, "profiles", "traffic_r2.json")
+    if not os.path.exists(path):
+        path = os.path.join(ROOT, "profiles", "traffic_r1.json")
     try:
         return json.load(open(path))
     except Exception:
@@ -413,18 +415,45 @@ def run_gpu_arm(args):
     if not args.no_e2e:
         e2e = run_e2e(args, pkg, dev, sets, calls, B, C, H, W, world, dist if world > 1 else None)
 
-    # ---- warp (config 4) on the same device, reported beside the headline -------------------
+    # free the headline tensors before the other configurations (config 5 alone needs ~16 GB)
+    del sets
+    torch.cuda.empty_cache()
+    peaks, peak_src = _peaks()
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    fp32_peak, probe_mhz = pkg.fp32_peak_probe()
+
+    # ---- config 5 (every rank takes part: strong scaling over the 98 targets) and its host-buffer form
+    c5 = c5_host = None
+    if not args.no_stack:
+        c5 = run_c5_stack(pkg, dev, rank, world, dist if world > 1 else None, args.sections, args.section_size)
+        if e2e is not None:
+            c5_host = run_c5_stack(pkg, dev, rank, world, dist if world > 1 else None, args.sections, args.section_size, to_host=True)
+
+    # ---- warp (configs 4 / 5), the other BASELINE configurations, section-8f rows: rank 0, beside the headline
     warp = run_warp(args, pkg, dev) if not args.no_warp else None
     tail = run_tail(pkg, dev, B, H, W) if (not args.no_warp and rank == 0) else None
     simu = run_simu_sff(pkg, dev) if (not args.no_warp and rank == 0) else None
-
+    configs = None
+    if not args.no_warp and rank == 0:
+        configs = {}
+        configs.update(run_c2_c4_sepconv(pkg, dev, fp32_peak, hbm))
+        configs.update(run_c4_warps(pkg, dev, hbm))
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+    if configs is not None:
+        configs["c1_simu_sff"] = simu
+        configs["c3_train_step"] = "the headline (value / roofline / rooflines)"
+        configs["c5_stack"] = c5
+        if c5_host is not None:
+            configs["c5_stack_host_out"] = c5_host
+    if e2e is not None and c5_host is not None:
+        e2e["e2e_u8"] = {"what": "config 5 through restore_stack with HOST buffers both ways: uint8 sections in pinned memory -> restored uint8 "
+                                 "sections in pinned memory (1 byte per pixel up per section, 3 bytes per target down; every rank keeps its own targets)",
+                         "mpix_per_s": c5_host["mpix_per_s"], "sections_per_s": c5_host["sections_per_s"], "seconds": c5_host["seconds"],
+                         "h2d_bytes_rank0": c5_host["h2d_bytes_rank0"], "d2h_bytes_rank0": c5_host["d2h_bytes_rank0"]}
 
-    peaks, peak_src = _peaks()
-    fp32_peak, probe_mhz = pkg.fp32_peak_probe()
     px_call = B * H * W
     fwd_tflops = FLOP_FWD(C) * px_call / (fwd_ms * 1e-3) / 1e12
     bwd_tflops = FLOP_BWD_TAPS(C) * px_call / (bwd_ms * 1e-3) / 1e12
@@ -437,7 +466,6 @@ def run_gpu_arm(args):
                              "flop_per_pixel": FLOP_BWD_TAPS(C), "traffic": None},
     }
     if warp:
-        hbm = float(peaks.get("hbm_gbs", 6650.0))
         rooflines["warp"] = {"bound": "hbm", "achieved": round(warp["gbs"], 1), "peak": hbm, "unit": "GB/s",
                              "frac": round(warp["gbs"] / hbm, 4), "ms_per_launch": round(warp["ms"], 5),
                              "bytes_per_pixel": BYTES_WARP(3), "traffic": None, "peak_source": peak_src}
@@ -470,7 +498,8 @@ def run_gpu_arm(args):
                          "cpu_model": _cpu_model(), "torch_threads": os.cpu_count()},
         "e2e": e2e, "gpu_launches": int(lsum.item()), "clocks": clocks,
         "extra": {"fwd_mpix_per_s": round(px_call / (fwd_ms * 1e-3) / 1e6, 1), "bwd_taps_mpix_per_s": round(px_call / (bwd_ms * 1e-3) / 1e6, 1),
-                  "warp": warp, "gray_x3_shortcut": gray, "fused_interp_tail": tail, "simu_sff_c1": simu, "ms_per_step_by_rank": per_rank},
+                  "configs": configs, "warp": warp, "gray_x3_shortcut": gray, "fused_interp_tail": tail, "simu_sff_c1": simu,
+                  "ms_per_step_by_rank": per_rank},
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -542,8 +571,17 @@ def run_e2e(args, pkg, dev, sets, calls, B, C, H, W, world, dist):
             os.sched_setaffinity(0, old_affinity)
         except Exception:
             pass
+    del host_in, host_out
+    ceil_s = run_copy_ceiling(dev, h2d, d2h, world, dist)
     return {"value": round(world * calls * B * H * W / (ms * 1e-3) / 1e6, 2), "unit": UNIT, "ms_per_step": round(ms, 3),
             "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": steps, "matches_device_path": same,
+            "copy_ceiling": {"what": "the same H2D and D2H byte counts per step as raw pinned-memory copies on two streams, no kernels "
+                                     "(max over ranks): the host link's own limit for this step",
+                             "ms_per_step": round(ceil_s * 1e3, 3), "mpix_per_s": round(world * calls * B * H * W / ceil_s / 1e6, 2),
+                             "gb_per_s_per_gpu_both_directions": round((h2d + d2h) / ceil_s / 1e9, 1),
+                             "e2e_fraction_of_ceiling": round(ceil_s * 1e3 / ms, 3)},
+            "note": "the e2e step ships 816 B/pixel of taps up and 816 B/pixel of tap gradients down -- traffic that does not exist in the "
+                    "reference pipeline (taps are produced and consumed on the GPU); `e2e_u8` is the stack job with uint8 on the wire",
             "cpus_bound_near_gpu": numa_cpus,
             "api": "sepconv_forward_backward_host(pinned input, vertical, horizontal, grad_output) -> pinned output, grad_vertical, "
                    "grad_horizontal; two samples per chunk on 3 streams (H2D, C-ABI fwd+bwd kernels, D2H overlapped); the step's two calls are queued back to back and joined once"}
@@ -589,6 +627,173 @@ def run_warp(args, pkg, dev):
                       "(gen_flow, seed 555); 3 rotating buffer sets (1.6 GB > L2); through the SpatialTransformation module",
             "c4_2048": {"gbs": g(2048, ms4), "ms": ms4, "gpix_per_s": 2048 * 2048 / (ms4 * 1e-3) / 1e9,
                         "config": "c4 warp: im[1,3,2048,2048], same flow family; 6 rotating buffer sets (805 MB > L2)"}}
+
+
+
+def _events_ms(fn, reps, warm=3):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def run_c2_c4_sepconv(pkg, dev, fp32_peak, hbm_gbs):
+    """BASELINE configs 2 and 4 (sepconv part): forward of one 256x256 section (C = 1 literal, C = 3 as the reference
+    calls it) and of one 2048x2048 section, unit-scale taps, rotating input sets larger than L2."""
+    import torch
+    sep = pkg.SeparableConvolution.apply
+    gen = torch.Generator(device=dev).manual_seed(77)
+    res = {}
+    for name, C, n, nsets, reps in (("c2_fwd_c1", 1, 256, 6, 50), ("c2_fwd_c3", 3, 256, 6, 50), ("c4_sepconv_fwd_2048", 3, 2048, 2, 5)):
+        sets = []
+        for _ in range(nsets):
+            inp = torch.rand((1, C, n + 50, n + 50), device=dev, generator=gen)
+            v = torch.softmax(torch.randn((1, K, n, n), device=dev, generator=gen), 1)
+            h = torch.softmax(torch.randn((1, K, n, n), device=dev, generator=gen), 1)
+            sets.append((inp, v, h))
+
+        def step():
+            for inp, v, h in sets:
+                sep(inp, v, h)
+        ms = _events_ms(step, reps) / nsets
+        tf = FLOP_FWD(C) * n * n / (ms * 1e-3) / 1e12
+        tap_gbs = 408.0 * n * n / (ms * 1e-3) / 1e9
+        res[name] = {"input": [1, C, n + 50, n + 50], "ms_per_call": round(ms, 5), "mpix_per_s": round(n * n / (ms * 1e-3) / 1e6, 1),
+                     "tflops": round(tf, 3), "frac_fp32_probe": round(tf / fp32_peak, 4), "taps_gb_per_s": round(tap_gbs, 1),
+                     "frac_hbm_taps": round(tap_gbs / hbm_gbs, 4), "l2": f"{nsets} rotating input sets ({nsets * 2 * K * n * n * 4 / 1e6:.0f} MB of taps)"}
+        if n == 256:
+            res[name]["note"] = "one 256x256 section is 512 CTA tiles on 148 SMs: launch / tail-latency bound, neither roofline applies"
+        del sets
+        torch.cuda.empty_cache()
+    return res
+
+
+def run_c4_warps(pkg, dev, hbm_gbs):
+    """BASELINE config 4 (warp part): im[1,3,2048,2048], planar-strided flow view; SFF fold flow and the N(0, 5 px) flow."""
+    import numpy as np
+    import torch
+    from sstem_restoration_b200 import synth
+    st = pkg.SpatialTransformation(True)
+    n, nsets, reps = 2048, 6, 20
+    sec = torch.from_numpy(synth.em_section(n, n, 50).astype(np.float32) / 255.0).to(dev)
+    res = {}
+    for name, flow_np in (("c4_warp_fold", synth.random_fold_flow(n, n, 555)[0]), ("c4_warp_noise5px", synth.noise_flow(n, n, 5.0))):
+        planar0 = torch.from_numpy(np.ascontiguousarray(flow_np.transpose(2, 0, 1))[None]).to(dev)
+        bufs = []
+        for i in range(nsets):
+            im = torch.roll(sec, shifts=17 * i, dims=1)[None, None].expand(1, 3, n, n).contiguous()
+            bufs.append((im, (planar0 + 0.01 * i).permute(0, 2, 3, 1)))
+
+        def step():
+            for im, fl in bufs:
+                st(im, fl)
+        ms = _events_ms(step, reps, warm=5) / nsets
+        gbs = BYTES_WARP(3) * n * n / (ms * 1e-3) / 1e9
+        res[name] = {"ms_per_call": round(ms, 5), "gb_per_s": round(gbs, 1), "frac_hbm": round(gbs / hbm_gbs, 4),
+                     "gpix_per_s": round(n * n / (ms * 1e-3) / 1e9, 2), "l2": f"{nsets} rotating buffer sets ({nsets * 134} MB)"}
+        del bufs
+        torch.cuda.empty_cache()
+    return res
+
+
+def run_c5_stack(pkg, dev, rank, world, dist, sections=100, size=4096, to_host=False):
+    """BASELINE config 5: a synthetic 100-section 4096x4096 stack, 98 targets (k-1, k+1) -> k
+    (sff_scripts_interp/inference.py:69-70) through restore_stack: uint8 sections uploaded from pinned host memory
+    inside the timed region, fused interpolation tail + flow warp + stitch per target, targets sharded contiguously
+    over the ranks (STRONG scaling: the job is fixed), restored uint8 sections gathered to rank 0.  Taps / flow are
+    synthetic and reused for every target (the KPN and the flow net are out of scope; their values do not affect speed)."""
+    import numpy as np
+    import torch
+    from sstem_restoration_b200 import shard, synth
+    H = W = size
+    gen = torch.Generator(device=dev).manual_seed(4321 + rank)
+    taps = [torch.softmax(torch.randn((1, K, H, W), device=dev, generator=gen), 1) for _ in range(4)]
+    flow_np, _ = synth.random_fold_flow(H, W, 555)
+    flow = torch.from_numpy(np.ascontiguousarray(flow_np.transpose(2, 0, 1))[None]).to(dev).permute(0, 2, 3, 1)
+    tile = synth.em_section(min(H, 1024), min(W, 1024), 0)
+    base = torch.from_numpy(np.tile(tile, (H // tile.shape[0], W // tile.shape[1])))
+    targets = shard.stack_targets(sections)
+    lo, hi = shard.shard_range(len(targets), rank, world)
+    stack = torch.empty((sections, H, W), dtype=torch.uint8).pin_memory()
+    for k in range(max(lo, 0), min(hi + 2, sections)):       # only the sections this rank touches are materialised
+        stack[k] = torch.roll(base, shifts=7 * k, dims=1)
+    pkg.set_gray_replicated("assert")                         # sections are gray x3 by construction (inference.py:71-74)
+    try:
+        kw = dict(rank=rank, world_size=world, dst=0, device=dev, to_host=to_host)
+        if to_host:                                            # pinned result buffers exist before the timed region, like the stack
+            kw["host_out"] = {n: torch.empty((hi - lo, H, W), dtype=torch.uint8).pin_memory() for n in ("interp", "warped", "stitch")}
+        warm = torch.empty((4, H, W), dtype=torch.uint8).pin_memory()
+        warm[:] = stack[lo:lo + 4] if hi - lo >= 2 else 0
+        pkg.restore_stack(warm, lambda k, x: taps, lambda k, xk, interp: flow, rank=0, world_size=1, device=dev)   # warm-up
+        if world > 1:
+            shard.gather_sections(torch.zeros((1, 8, 8), dtype=torch.uint8, device=dev), world, dst=0)             # communicator
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        out = pkg.restore_stack(stack, lambda k, x: taps, lambda k, xk, interp: flow, **kw)
+        e1.record()
+        torch.cuda.synchronize()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+    finally:
+        pkg.set_gray_replicated("off")
+    ms = torch.tensor([max(e0.elapsed_time(e1), wall_ms if to_host else 0.0)], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    sec = float(ms.item()) * 1e-3
+    per_rank_max = -(-len(targets) // world)
+    st = out["stats"]
+    res = {"workload": f"{sections} sections {H}x{W}, {len(targets)} targets", "n_gpus": world, "scaling": "strong",
+           "seconds": round(sec, 4), "sections_per_s": round(len(targets) / sec, 2), "mpix_per_s": round(len(targets) * H * W / sec / 1e6, 1),
+           "targets_on_busiest_rank": per_rank_max, "ideal_speedup_at_this_n": round(len(targets) / per_rank_max, 3),
+           "ms_per_target_on_busiest_rank": round(sec * 1e3 / per_rank_max, 3),
+           "h2d_bytes_rank0": st["h2d_bytes"], "d2h_bytes_rank0": st["d2h_bytes"], "kernel_launches_rank0": st["kernel_launches"],
+           "outputs": ("interp, warped, stitch: uint8, each rank downloads its own targets into pinned host memory (one async copy per target, no collective)"
+                       if to_host else "interp, warped, stitch: uint8 [98,H,W] each, gathered to rank 0 (device memory)"),
+           "api": "sstem_restoration_b200.restore_stack(stack_u8_pinned, taps_fn, flow_fn, rank, world_size, dst=0)"}
+    del taps, flow, stack, out
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_copy_ceiling(dev, h2d_bytes, d2h_bytes, world, dist, chunks=8, steps=3):
+    """What the host link alone allows for the e2e step: the same byte counts, pinned buffers, H2D and D2H running
+    concurrently on two streams, no kernels.  -> seconds per step (max over ranks)."""
+    import torch
+    n_up, n_dn = h2d_bytes // chunks, d2h_bytes // chunks
+    hu, hd = torch.empty(n_up, dtype=torch.uint8).pin_memory(), torch.empty(n_dn, dtype=torch.uint8).pin_memory()
+    du, dd = torch.empty(n_up, dtype=torch.uint8, device=dev), torch.empty(n_dn, dtype=torch.uint8, device=dev)
+    s_up, s_dn = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    def step():
+        for _ in range(chunks):
+            with torch.cuda.stream(s_up):
+                du.copy_(hu, non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                hd.copy_(dd, non_blocking=True)
+        s_up.synchronize()
+        s_dn.synchronize()
+    step()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    t = torch.tensor([dt], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
 
 
 def run_tail(pkg, dev, B, H, W, reps=5):
@@ -640,6 +845,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-warp", action="store_true")
     ap.add_argument("--no-gather", action="store_true", help="diagnostic: skip the output gather at N > 1")
+    ap.add_argument("--no-stack", action="store_true", help="skip BASELINE config 5 (the 100-section stack job)")
+    ap.add_argument("--sections", type=int, default=100)
+    ap.add_argument("--section-size", type=int, default=4096)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -95,7 +95,7 @@ class _SectionCache:
 
 def restore_stack(stack: torch.Tensor, taps_fn: Callable, flow_fn: Optional[Callable] = None, *,
                   rank: int = 0, world_size: int = 1, group=None, dst: Optional[int] = 0, device=None,
-                  prefetch: int = 3, to_host: bool = False):
+                  prefetch: int = 3, to_host: bool = False, host_out: Optional[dict] = None):
     """Restore the interior sections of ``stack`` (uint8 ``[N,H,W]``, pinned host memory or CUDA).
 
     For every target k in 1..N-2 owned by this rank::
@@ -108,9 +108,13 @@ def restore_stack(stack: torch.Tensor, taps_fn: Callable, flow_fn: Optional[Call
             warped = SpatialTransformation()(xk, flow_fn(k, xk, interp))   # flow [1,H,W,2], any strides
             warped_gray, stitch = warp_stitch(warped, interp)
 
-    Returns a dict of uint8 ``[N-2,H,W]`` tensors -- ``interp`` and, with ``flow_fn``, ``warped`` and ``stitch`` --
-    gathered to rank ``dst`` (every rank when ``dst`` is None; other ranks get ``None``), plus ``stats``.
-    ``to_host=True`` downloads the gathered result into pinned host memory (1 byte per pixel) before returning.
+    Returns a dict of uint8 tensors -- ``interp`` and, with ``flow_fn``, ``warped`` and ``stitch`` -- plus ``stats``.
+
+    ``to_host=False`` (default): device tensors ``[N-2,H,W]`` gathered to rank ``dst`` (every rank when ``dst`` is None;
+    other ranks get ``None``) -- the path's only collective.
+    ``to_host=True``: every rank downloads ITS OWN targets (what a rank would hand to its PNG writers) into pinned host
+    tensors ``[n_local,H,W]`` -- ``host_out`` may supply them -- one asynchronous copy per target on a download stream,
+    overlapped with the next target's kernels; no collective; the call returns when the copies have completed.
     """
     if not torch.cuda.is_available():
         raise _lib.SstemError("restore_stack: no CUDA device; there is no CPU fallback")
@@ -128,6 +132,13 @@ def restore_stack(stack: torch.Tensor, taps_fn: Callable, flow_fn: Optional[Call
     warp = SpatialTransformation(True)
     names = ("interp",) + (("warped", "stitch") if flow_fn is not None else ())
     local = {n: torch.empty((len(mine), H, W), dtype=torch.uint8, device=dev) for n in names}
+    host = None
+    if to_host:
+        host = host_out if host_out is not None else {n: torch.empty((len(mine), H, W), dtype=torch.uint8).pin_memory() for n in names}
+        for n in names:
+            if tuple(host[n].shape) != (len(mine), H, W) or host[n].dtype != torch.uint8 or host[n].is_cuda:
+                raise ValueError(f"restore_stack: host_out[{n!r}] must be a CPU uint8 tensor [{len(mine)},{H},{W}]")
+        down = torch.cuda.Stream(device=dev)
     with torch.cuda.device(dev), torch.no_grad():
         for j in range(min(prefetch, len(mine))):
             for k in mine[j]:
@@ -140,22 +151,25 @@ def restore_stack(stack: torch.Tensor, taps_fn: Callable, flow_fn: Optional[Call
             k1v, k1h, k2v, k2h = taps_fn(k, x)
             interp = prediction_to_uint8(interpolation_tail(x[:, :3], x[:, 3:6], k1v, k1h, k2v, k2h), 0, out=local["interp"][i:i + 1])
             if flow_fn is not None:
-                sk = cache.get(k)
-                xk = sections_to_input(sk, None, 0)
+                xk = sections_to_input(cache.get(k), None, 0)
                 warped = warp(xk, flow_fn(k, xk, interp))
                 warp_stitch(warped, interp, out=(local["warped"][i:i + 1], local["stitch"][i:i + 1]))
+            if to_host:
+                done = torch.cuda.Event()
+                done.record()
+                with torch.cuda.stream(down):
+                    down.wait_event(done)
+                    for n in names:
+                        host[n][i].copy_(local[n][i], non_blocking=True)
             cache.drop_below(ka)
         out = {}
-        for n in names:
-            full = shard.gather_sections(local[n], len(targets), group=group, dst=dst) if world_size > 1 else local[n]
-            if full is not None and to_host:
-                host = torch.empty(full.shape, dtype=torch.uint8).pin_memory()
-                host.copy_(full, non_blocking=True)
-                full = host
-            out[n] = full
         if to_host:
-            torch.cuda.current_stream(dev).synchronize()
+            down.synchronize()
+            out.update({n: host[n] for n in names})
+        else:
+            for n in names:
+                out[n] = shard.gather_sections(local[n], len(targets), group=group, dst=dst) if world_size > 1 else local[n]
     out["stats"] = {"targets": len(targets), "targets_this_rank": len(mine), "h2d_bytes": cache.h2d_bytes,
-                    "d2h_bytes": sum(int(out[n].numel()) for n in names if to_host and out[n] is not None),
+                    "d2h_bytes": sum(int(host[n].numel()) for n in names) if to_host else 0,
                     "kernel_launches": _lib.launch_count() - n0}
     return out

@@ -111,6 +111,7 @@ def test_restore_stack_matches_the_op_by_op_expression():
         gray, stitch = oracle.warp_stitch_restated(warped[0].cpu().numpy(), interp[0].cpu().numpy())
         assert torch.equal(res["interp"][i], interp[0].cpu())
         assert np.array_equal(res["warped"][i].numpy(), gray) and np.array_equal(res["stitch"][i].numpy(), stitch)
+    assert not res["interp"].is_cuda and res["stats"]["d2h_bytes"] == 3 * 4 * H * W
     on_dev = pkg.restore_stack(stack.cuda(), taps_fn, None)
     assert set(on_dev) == {"interp", "stats"} and torch.equal(on_dev["interp"].cpu(), res["interp"])
     # the per-rank shards of a 3-way split (no process group here: each call returns its own shard) tile the result
