@@ -310,6 +310,9 @@ def run_gpu_arm(args):
     comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
     comm_done = [None, None]
     step_no = [0]
+    gatherer = None
+    if world > 1 and not args.no_gather:
+        gatherer = shard.SectionGatherer((C, H, W), torch.float32, calls * B, dev, dst=0, force_collective=args.nccl_gather)
 
     def step(record=False):
         outs = []
@@ -335,7 +338,7 @@ def run_gpu_arm(args):
             with torch.cuda.stream(comm_stream):
                 comm_stream.wait_event(ready)
                 local.record_stream(comm_stream)
-                shard.gather_sections(local, world * calls * B, dst=0)   # to rank 0, as DataParallel does
+                gatherer.gather(local)                     # to rank 0, as DataParallel does (copy-engine peer writes)
                 comm_done[k] = torch.cuda.Event()
                 comm_done[k].record(comm_stream)
             step_no[0] += 1
@@ -491,7 +494,8 @@ def run_gpu_arm(args):
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "c3_train_step", "calls_per_step": calls, "input": [B, C, H + 50, W + 50],
-                   "taps": [B, K, H, W], "pixels_per_step_per_gpu": pix_per_step, "parallelism": f"dp{world} (batch shards, no data-path collective; outputs gathered to rank 0 on a side stream)",
+                   "taps": [B, K, H, W], "pixels_per_step_per_gpu": pix_per_step, "parallelism": f"dp{world} (batch shards, no data-path collective; outputs gathered to rank 0 on a side stream"
+                                  + (f", {gatherer.mode}" + (f" [{gatherer.why}]" if gatherer.why else "") if gatherer is not None else "") + ")",
                    "l2": "working set 7 GB per step >> 126 MB L2 (no flush needed)"},
         "roofline": roof, "rooflines": rooflines,
         "cpu_baseline": {"value": round(cpu_val, 4), "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": cpu_sample,
@@ -845,6 +849,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-warp", action="store_true")
     ap.add_argument("--no-gather", action="store_true", help="diagnostic: skip the output gather at N > 1")
+    ap.add_argument("--nccl-gather", action="store_true", help="diagnostic: gather with the NCCL collective instead of copy-engine peer writes")
     ap.add_argument("--no-stack", action="store_true", help="skip BASELINE config 5 (the 100-section stack job)")
     ap.add_argument("--sections", type=int, default=100)
     ap.add_argument("--section-size", type=int, default=4096)

@@ -117,3 +117,47 @@ def test_restore_stack_matches_the_op_by_op_expression():
     # the per-rank shards of a 3-way split (no process group here: each call returns its own shard) tile the result
     parts = [pkg.restore_stack(stack.cuda(), taps_fn, None, rank=r, world_size=3)["interp"] for r in range(3)]
     assert [p.shape[0] for p in parts] == [2, 1, 1] and torch.equal(torch.cat(parts), on_dev["interp"])
+
+
+def _gather_worker(rank, world, port, q):
+    import os
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from sstem_restoration_b200 import shard
+    g = shard.SectionGatherer((3, 8, 8), torch.float32, 2, dev, dst=0)
+    ok = True
+    for rep in range(3):
+        local = torch.stack([torch.full((3, 8, 8), float(10 * rank + j + rep), device=dev) for j in range(2)])
+        got = g.gather(local)
+        torch.cuda.synchronize()
+        if rank == 0:
+            ok = ok and [float(got[i, 0, 0, 0]) for i in range(2 * world)] == [float(10 * r + j + rep) for r in range(world) for j in range(2)]
+        else:
+            ok = ok and got is None
+    q.put((rank, ok, g.mode, g.why))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_section_gatherer_peer_writes_on_two_gpus():
+    """SectionGatherer on real GPUs: symmetric-memory peer writes (or, where the driver refuses, the NCCL fall-back) give
+    the units in rank order on dst, repeatedly."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] for r in res), res
+    print("SectionGatherer mode:", res[0][2], res[0][3])

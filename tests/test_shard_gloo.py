@@ -37,6 +37,17 @@ def _worker(rank, world, port, n_units, q):
         ok = ok and u8.dtype == torch.uint8 and u8.shape == (n_units, 2, 3) and all(bool((u8[k] == k).all()) for k in range(n_units))
     else:
         ok = ok and u8 is None
+    # SectionGatherer (bench.py's per-step output gather): on CPU / gloo it must fall back to the collective, twice in a
+    # row (its device path alternates two buffers), and return the units in rank order on dst only
+    g = shard.SectionGatherer((2, 3), torch.float32, 2, "cpu", dst=0)
+    ok = ok and g.mode == "collective"
+    for rep in range(2):
+        got = g.gather(torch.stack([torch.full((2, 3), float(10 * rank + j + rep)) for j in range(2)]))
+        if rank == 0:
+            ok = ok and got.shape == (2 * world, 2, 3) and [float(got[i, 0, 0]) for i in range(4)] == [0. + rep, 1. + rep, 10. + rep, 11. + rep]
+        else:
+            ok = ok and got is None
+    # restore_stack's host logic without a GPU is refused loudly (no CPU fallback)
     # timing reduction used by bench.py: max over ranks
     t = torch.tensor([float(rank + 1)])
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
