@@ -254,6 +254,25 @@ int sstem_warp_stitch_u8(const float* warped, const uint8_t* interp, uint8_t* gr
                          int64_t B, int64_t C, int64_t H, int64_t W, void* stream);
 
 /*
+ * Tile-major taps (the layout a tap PRODUCER should emit -- the last Conv2d(51,51,3x3) of
+ * IFNet._kernel_module, sff_scripts_interp/model/model_interp.py:129-137, writes [B,51,H,W] today and sepconv re-reads it
+ * as 51 x 8 row segments of 32 bytes per 8x8 pixel tile):
+ *
+ *     tiled[b][ty][tx][tap][row][col] = taps[b][tap][8*ty + row][8*tx + col]     (0 outside the image)
+ *     ty < ceil(H/8), tx < ceil(W/8), tap < 51, row < 8, col < 8
+ *
+ * i.e. all 51 taps of an 8x8 pixel tile are 13 056 contiguous bytes -- one bulk copy for the consuming warp.
+ * sstem_taps_tiled_elems: floats to allocate.  sstem_taps_to_tiled: conversion for producers that cannot emit it directly
+ * (and for the parity tests).  sstem_sepconv_forward_tiled: the forward of sstem_sepconv_forward with both tap tensors in
+ * this layout (K must be 51; flags: SSTEM_SEPCONV_GRAY_REPLICATED); results are bit-identical to the [B,51,H,W] path.
+ */
+int64_t sstem_taps_tiled_elems(int64_t B, int64_t H, int64_t W);
+int sstem_taps_to_tiled(const float* taps, float* tiled, int64_t B, int64_t H, int64_t W, void* stream);
+int sstem_sepconv_forward_tiled(const float* input, const float* vertical_tiled, const float* horizontal_tiled,
+                                float* output, int64_t B, int64_t C, int64_t H, int64_t W,
+                                int32_t K, uint32_t flags, void* stream);
+
+/*
  * FP32 FMA-pipe probe: runs a register-resident FFMA loop on every SM of the
  * current device and returns the sustained rate in TFLOP/s (2 flop per FMA).
  * bench.py uses it as the measured denominator of the sepconv roofline

@@ -15,7 +15,7 @@ __graft_entry__.build) every operator raises.
 from ._lib import SstemError, launch_count, fp32_peak_probe  # noqa: F401
 from .sepconv import (  # noqa: F401
     SeparableConvolution, FunctionSepconv, ModuleSepconv, set_strict_order, set_gray_replicated,
-    interpolation_tail, ModuleInterpolationTail,
+    interpolation_tail, ModuleInterpolationTail, taps_to_tiled, sepconv_forward_tiled,
 )
 from .warp import SpatialTransformation, image_warp  # noqa: F401
 from .host import sepconv_forward_backward_host, join_host_pipeline  # noqa: F401
@@ -25,7 +25,7 @@ from . import shard, synth, sff_sim  # noqa: F401
 
 __all__ = [
     "SeparableConvolution", "FunctionSepconv", "ModuleSepconv", "set_strict_order", "set_gray_replicated",
-    "interpolation_tail", "ModuleInterpolationTail",
+    "interpolation_tail", "ModuleInterpolationTail", "taps_to_tiled", "sepconv_forward_tiled",
     "SpatialTransformation", "image_warp", "sepconv_forward_backward_host", "join_host_pipeline", "SstemError", "launch_count", "fp32_peak_probe",
     "sections_to_input", "prediction_to_uint8", "restore_stack", "warp_stitch", "shard", "synth", "sff_sim",
 ]

@@ -84,5 +84,7 @@ int try_launch_bwd_taps_k51_v2(const float* g, const float* in, const float* v, 
                                int64_t B, int C, int c0, int H, int W, int accumulate, cudaStream_t s);
 int try_launch_fwd_k51_v3(const float* in, const float* v, const float* h, float* out,
                           int64_t B, int C, int c0, int H, int W, cudaStream_t s);
+int try_launch_fwd_k51_v3_c1(const float* in, const float* v, const float* h, float* out,
+                             int64_t B, int C, int c0, int H, int W, int replicas, cudaStream_t s);
 
 }  // namespace sstem

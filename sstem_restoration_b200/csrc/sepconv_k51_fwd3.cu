@@ -1,46 +1,65 @@
-// Launcher of the third-generation forward kernel (device code in sepconv_k51_v3.cuh): repack the input
-// channel-interleaved into a stream-ordered workspace, encode the tensor maps, launch the persistent grid.
+// Launchers of the third-generation forward kernel (device code in sepconv_k51_v3.cuh): copy the input into the layout
+// the window loads want (channel-interleaved for 3 channels, 16-byte pitch for 1) in a stream-ordered workspace, encode
+// the tensor maps, launch the persistent grid.  Also the tile-major tap layout of SURVEY 8f N2 (sstem_taps_to_tiled,
+// sstem_sepconv_forward_tiled).
 #include "sepconv_k51_v3.cuh"
 
 #include <stdlib.h>
 
 namespace sstem {
+namespace {
 
-// returns 0 on launch, > 0 CUDA error, -1000 when the path does not apply (caller runs the first-generation kernel)
-int try_launch_fwd_k51_v3(const float* in, const float* v, const float* h, float* out,
-                          int64_t B, int C, int c0, int H, int W, cudaStream_t s) {
-    static const int gen = getenv("SSTEM_FWD_GEN") ? atoi(getenv("SSTEM_FWD_GEN")) : 3;   // experiments: force generation 1
-    if (gen < 3 || (W & 3) || !aligned16(v) || !aligned16(h)) return -1000;
+// returns 0 on launch, > 0 CUDA error, -1000 when the path does not apply
+template <int CC, bool TILED>
+int launch_fwd_v3(const float* in, const float* v, const float* h, float* out,
+                  int64_t B, int C, int c0, int H, int W, int replicas, bool force, cudaStream_t s) {
+    if (!TILED && ((W & 3) || !aligned16(v) || !aligned16(h))) return -1000;
+    if (TILED && (!aligned16(v) || !aligned16(h))) return SSTEM_E_ALIGN;
     const int64_t tiles_x = (W + V3_COLS * V3_WARPS - 1) / (V3_COLS * V3_WARPS), tiles_y = (H + F3_R - 1) / F3_R;
     if (tiles_x * tiles_y * B > INT32_MAX / 2) return -1000;
     // a persistent grid needs several tiles per warp to balance; small problems stay on the CTA-per-tile kernel
     static const int64_t min_tiles = getenv("SSTEM_V3_MIN_TILES") ? atoll(getenv("SSTEM_V3_MIN_TILES")) : 10;   // measured crossover: ~10 tiles per warp (forward), ~6 (tap gradients)
-    if (tiles_x * tiles_y * B < min_tiles * 2 * sm_count()) return -1000;
+    if (!force && tiles_x * tiles_y * B < min_tiles * 2 * sm_count()) return -1000;
     const int64_t IH = H + K51 - 1, IW = W + K51 - 1, plane = (int64_t)H * W;
+    const int64_t IWP = (IW + 3) & ~(int64_t)3;              // CC == 1: row pitch of the plane copy
     float* ws = nullptr;
-    const size_t ws_bytes = (size_t)(B * IH * IW) * 16;
+    const size_t ws_bytes = CC == 3 ? (size_t)(B * IH * IW) * 16 : (size_t)(B * IH * IWP) * 4;
     if (workspace_alloc(reinterpret_cast<void**>(&ws), ws_bytes + 256, s)) return -1000;
     int* counter = reinterpret_cast<int*>(reinterpret_cast<char*>(ws) + ws_bytes);   // dynamic tile scheduler ticket
     cudaMemsetAsync(counter, 0, 256, s);
-    int e = launch_repack_nhwc4(in, ws, B, C, c0, IH, IW, s);
+    int e = 0;
+    if (CC == 3) e = launch_repack_nhwc4(in, ws, B, C, c0, IH, IW, s);
+    else {
+        const int64_t total = B * IH * IWP;
+        const unsigned blocks = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 16);
+        repack_plane_pitch_kernel<<<blocks, 256, 0, s>>>(in, ws, C, c0, (int)IH, (int)IW, (int)IWP, total);
+        count_launch();
+        e = finish_launch();
+    }
     CUtensorMap min, mv, mh;
     if (!e) {
-        const int64_t dims[3] = {4 * IW, IH, B}, strides[3] = {1, 4 * IW, 4 * IW * IH};
-        const int box[3] = {4 * V3_WIN_COLS, V3_GROUP, 1};
-        const int64_t tdims[4] = {W, H, K51, B}, tstrides[4] = {1, W, plane, (int64_t)K51 * plane};
-        const int vbox[4] = {V3_COLS, F3_R, V3_GROUP, 1}, hbox[4] = {V3_COLS, F3_R, K51, 1};
-        if (!make_map_f32(&min, ws, 3, dims, strides, box) || !make_map_f32(&mv, v, 4, tdims, tstrides, vbox) ||
-            !make_map_f32(&mh, h, 4, tdims, tstrides, hbox))
-            e = -1000;
+        const int64_t row = CC == 3 ? 4 * IW : IWP;
+        const int64_t dims[3] = {row, IH, B}, strides[3] = {1, row, row * IH};
+        const int box[3] = {(CC == 3 ? 4 : 1) * V3_WIN_COLS, V3_GROUP, 1};
+        if (!make_map_f32(&min, ws, 3, dims, strides, box)) e = -1000;
+        if (!e && !TILED) {
+            const int64_t tdims[4] = {W, H, K51, B}, tstrides[4] = {1, W, plane, (int64_t)K51 * plane};
+            const int vbox[4] = {V3_COLS, F3_R, V3_GROUP, 1}, hbox[4] = {V3_COLS, F3_R, K51, 1};
+            if (!make_map_f32(&mv, v, 4, tdims, tstrides, vbox) || !make_map_f32(&mh, h, 4, tdims, tstrides, hbox)) e = -1000;
+        } else if (!e) {
+            mv = min;                                      // unused by the kernel, but must be valid objects to copy
+            mh = min;
+        }
     }
     if (!e) {
         static PerDeviceOnce done;
-        auto kern = sepconv_fwd_k51_v3_kernel;
+        auto kern = sepconv_fwd_k51_v3_kernel<CC, TILED>;
         e = set_smem_once(kern, F3_SMEM, done);
         if (!e) {
             V3Shape sh{H, W, (int)tiles_x, (int)tiles_y, (int)(tiles_x * tiles_y * B), C, c0};
+            F3Tiled tl{TILED ? v : nullptr, TILED ? h : nullptr, (int)((W + 7) / 8), (int)((H + 7) / 8)};
             const int ctas = (int)std::min<int64_t>(2 * (int64_t)sm_count(), (int64_t)sh.ntiles);
-            kern<<<ctas, V3_WARPS * 32, F3_SMEM, s>>>(min, mv, mh, out, counter, sh);
+            kern<<<ctas, V3_WARPS * 32, F3_SMEM, s>>>(min, mv, mh, tl, out, counter, sh, replicas);
             count_launch();
             e = finish_launch();
         }
@@ -49,4 +68,73 @@ int try_launch_fwd_k51_v3(const float* in, const float* v, const float* h, float
     return e;
 }
 
+bool fwd_gen3_enabled() {
+    static const int gen = getenv("SSTEM_FWD_GEN") ? atoi(getenv("SSTEM_FWD_GEN")) : 3;   // experiments: force generation 1
+    return gen >= 3;
+}
+
+}  // namespace
+
+int try_launch_fwd_k51_v3(const float* in, const float* v, const float* h, float* out,
+                          int64_t B, int C, int c0, int H, int W, cudaStream_t s) {
+    if (!fwd_gen3_enabled()) return -1000;
+    return launch_fwd_v3<3, false>(in, v, h, out, B, C, c0, H, W, 1, false, s);
+}
+
+// one channel (plane c0), written to `replicas` consecutive output planes (gray x3 shortcut: replicas = C)
+int try_launch_fwd_k51_v3_c1(const float* in, const float* v, const float* h, float* out,
+                             int64_t B, int C, int c0, int H, int W, int replicas, cudaStream_t s) {
+    // Measured (16x3x512^2 gray x3): generation 1 0.700 ms, this kernel 0.718 ms on [B,51,H,W] taps and 0.685 ms on tile-major
+    // taps -- at one channel a step has only 56 FFMA2 to hide its 21 LDS and the ring bookkeeping behind, so the
+    // persistent kernel pays off only with the cheaper tiled tap delivery.  Kept selectable for experiments.
+    static const bool on = getenv("SSTEM_FWD_C1_GEN") && atoi(getenv("SSTEM_FWD_C1_GEN")) >= 3;
+    if (!on || !fwd_gen3_enabled()) return -1000;
+    return launch_fwd_v3<1, false>(in, v, h, out, B, C, c0, H, W, replicas, false, s);
+}
+
 }  // namespace sstem
+
+using namespace sstem;
+
+// ---- tile-major taps ---------------------------------------------------------------------------------
+extern "C" int64_t sstem_taps_tiled_elems(int64_t B, int64_t H, int64_t W) {
+    if (B <= 0 || H <= 0 || W <= 0) return 0;
+    return B * ((H + 7) / 8) * ((W + 7) / 8) * K51 * 64;
+}
+
+extern "C" int sstem_taps_to_tiled(const float* taps, float* tiled, int64_t B, int64_t H, int64_t W, void* stream) {
+    if (!taps || !tiled) return SSTEM_E_NULL;
+    if (B <= 0 || H <= 0 || W <= 0 || H > (1 << 24) || W > (1 << 24)) return SSTEM_E_SHAPE;
+    if (!aligned4(taps) || !aligned16(tiled)) return SSTEM_E_ALIGN;
+    DeviceGuard guard(tiled);
+    if (guard.err) return guard.err;
+    const int64_t total = sstem_taps_tiled_elems(B, H, W);
+    const unsigned blocks = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 32);
+    taps_to_tiled_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(taps, tiled, (int)H, (int)W, (int)((H + 7) / 8), (int)((W + 7) / 8), total);
+    count_launch();
+    return finish_launch();
+}
+
+extern "C" int sstem_sepconv_forward_tiled(const float* input, const float* vertical_tiled, const float* horizontal_tiled,
+                                           float* output, int64_t B, int64_t C, int64_t H, int64_t W,
+                                           int32_t K, uint32_t flags, void* stream) {
+    if (!input || !vertical_tiled || !horizontal_tiled || !output) return SSTEM_E_NULL;
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || C > 65535 || H > (1 << 24) || W > (1 << 24)) return SSTEM_E_SHAPE;
+    if (K != K51) return SSTEM_E_SHAPE;                    // the tiled layout is defined for the reference's 51 taps
+    if (flags & ~SSTEM_SEPCONV_GRAY_REPLICATED) return SSTEM_E_FLAG;
+    if (!aligned4(input) || !aligned4(output)) return SSTEM_E_ALIGN;
+    DeviceGuard guard(output);
+    if (guard.err) return guard.err;
+    cudaStream_t s = (cudaStream_t)stream;
+    int e = 0;
+    if ((flags & SSTEM_SEPCONV_GRAY_REPLICATED) && C > 1)
+        e = launch_fwd_v3<1, true>(input, vertical_tiled, horizontal_tiled, output, B, (int)C, 0, (int)H, (int)W, (int)C, true, s);
+    else {
+        int c0 = 0;
+        while (c0 < C && !e) {                             // channel chunks of 3, then single planes
+            if (C - c0 >= 3) { e = launch_fwd_v3<3, true>(input, vertical_tiled, horizontal_tiled, output, B, (int)C, c0, (int)H, (int)W, 1, true, s); c0 += 3; }
+            else { e = launch_fwd_v3<1, true>(input, vertical_tiled, horizontal_tiled, output, B, (int)C, c0, (int)H, (int)W, 1, true, s); c0 += 1; }
+        }
+    }
+    return e == -1000 ? SSTEM_E_SHAPE : e;
+}

@@ -59,6 +59,37 @@ repack_nchw3_to_nhwc4_kernel(const float* __restrict__ in, float4* __restrict__ 
     }
 }
 
+// One plane (channel c0) of in [B,C,IH,IW] -> out [B,IH,IWP] with the row pitch IWP rounded up to 4 floats, so that
+// the copy can be the source of a tensor map (16-byte strides); the pad columns are zero.
+__global__ void __launch_bounds__(256)
+repack_plane_pitch_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int c0, int IH, int IW, int IWP, int64_t total) {
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
+        const int x = (int)(i % IWP);
+        const int64_t r = i / IWP;
+        const int y = (int)(r % IH);
+        const int64_t b = r / IH;
+        out[i] = x < IW ? __ldg(in + ((b * C + c0) * IH + y) * (int64_t)IW + x) : 0.f;
+    }
+}
+
+// NCHW taps [B,51,H,W] -> tile-major [B][ceil(H/8)][ceil(W/8)][51][8][8] (zero outside the image): the layout the
+// TILED kernels consume.  One thread per output element; reads are 32-byte row segments.
+__global__ void __launch_bounds__(256)
+taps_to_tiled_kernel(const float* __restrict__ taps, float* __restrict__ tiled, int H, int W, int ty8, int tx8, int64_t total) {
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
+        const int col = (int)(i & 7), row = (int)((i >> 3) & 7);
+        int64_t r = i >> 6;
+        const int tap = (int)(r % K51); r /= K51;
+        const int tx = (int)(r % tx8); r /= tx8;
+        const int ty = (int)(r % ty8);
+        const int64_t b = r / ty8;
+        const int y = ty * 8 + row, x = tx * 8 + col;
+        tiled[i] = (y < H && x < W) ? __ldg(taps + ((b * K51 + tap) * H + y) * (int64_t)W + x) : 0.f;
+    }
+}
+
 #ifndef SSTEM_BWD2_TB
 #define SSTEM_BWD2_TB 7                                    // taps per block: NP * TB independent FFMA2 chains
 #endif

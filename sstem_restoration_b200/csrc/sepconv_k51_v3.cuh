@@ -88,6 +88,11 @@ __device__ __forceinline__ void tma_load_3d_a(unsigned dst, const CUtensorMap* m
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(policy) : "memory");
 }
+// 1-D bulk copy global -> shared (16-byte aligned, size a multiple of 16), completion on an mbarrier
+__device__ __forceinline__ void bulk_load_a(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
 __device__ __forceinline__ float lds_f32(unsigned addr) {
     float v;
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
@@ -374,9 +379,9 @@ constexpr unsigned F3_OFF_BAR = F3_OFF_H + F3_H_BYTES;           // 24832
 constexpr unsigned F3_WARP_BYTES = F3_OFF_BAR + 128;             // 24960 = 195 * 128
 constexpr size_t F3_SMEM = (size_t)V3_WARPS * F3_WARP_BYTES + 128;
 
-template <int S>
+template <int S, int CC>
 __device__ __forceinline__ void fwd3_step(unsigned pa, const unsigned (&va)[8], bool novalid,
-                                          const float2 (&h2)[4][13], float2 (&acc)[3][4]) {
+                                          const float2 (&h2)[4][13], float2 (&acc)[CC][4]) {
     constexpr int NP = 4, NT = 13;
     float2 v2[NP];
 #pragma unroll
@@ -386,17 +391,19 @@ __device__ __forceinline__ void fwd3_step(unsigned pa, const unsigned (&va)[8], 
         v2[pp].x = a_ok ? lds_f32(va[2 * pp]) : 0.f;
         v2[pp].y = b_ok ? lds_f32(va[2 * pp + 1]) : 0.f;
     }
-    float2 part[3][NP];
+    float2 part[CC][NP];
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
-        float4 P = lds_f32x4(pa + 64 * t);
+        float4 P;                                          // CC == 3: channel-interleaved window, one LDS.128 per tap;
+        if (CC == 3) P = lds_f32x4(pa + 64 * t);           // CC == 1: planar window, one LDS.32
+        else P = make_float4(lds_f32(pa + 16 * t), 0.f, 0.f, 0.f);
         if (t == NT - 1) {                                 // tap 51 does not exist (lanes g == 3)
             P.x = novalid ? 0.f : P.x;
             P.y = novalid ? 0.f : P.y;
             P.z = novalid ? 0.f : P.z;
         }
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
+        for (int c = 0; c < CC; ++c) {
             const float p = c == 0 ? P.x : (c == 1 ? P.y : P.z);
 #pragma unroll
             for (int pp = 0; pp < NP; ++pp) {
@@ -406,7 +413,7 @@ __device__ __forceinline__ void fwd3_step(unsigned pa, const unsigned (&va)[8], 
         }
     }
 #pragma unroll
-    for (int c = 0; c < 3; ++c)
+    for (int c = 0; c < CC; ++c)
 #pragma unroll
         for (int pp = 0; pp < NP; ++pp) {
             if (S >= 0) {
@@ -419,10 +426,21 @@ __device__ __forceinline__ void fwd3_step(unsigned pa, const unsigned (&va)[8], 
         }
 }
 
+// CC = 3: channel-interleaved window (float4 per pixel); CC = 1: one plane, copied to a 16-byte pitch (the gray x3
+// shortcut runs this and writes `replicas` identical output planes).  TILED: the taps arrive in the tile-major layout
+// [B][H/8][W/8][51][8][8] (what a tap producer should emit) -- a warp tile's horizontal taps are ONE
+// contiguous 13 KB bulk copy and a group of 4 vertical-tap planes one contiguous 1 KB -- instead of 51 x 8 row segments
+// of 32 bytes gathered by a tensor map from [B][51][H][W].
+struct F3Tiled {
+    const float* v;                                        // tile-major vertical / horizontal taps (TILED only)
+    const float* h;
+    int tiles_x8, tiles_y8;                                // warp tiles per row / column of the tiled layout
+};
+template <int CC, bool TILED>
 __global__ void __launch_bounds__(V3_WARPS * 32, 2)
 sepconv_fwd_k51_v3_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_v,
-                          const __grid_constant__ CUtensorMap map_h, float* __restrict__ out,
-                          int* __restrict__ next_tile_counter, const V3Shape sh) {
+                          const __grid_constant__ CUtensorMap map_h, const F3Tiled tl, float* __restrict__ out,
+                          int* __restrict__ next_tile_counter, const V3Shape sh, int replicas) {
     constexpr int G = 4, R = F3_R, NP = 4, NT = 13;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -456,20 +474,31 @@ sepconv_fwd_k51_v3_kernel(const __grid_constant__ CUtensorMap map_in, const __gr
         b = r / sh.tiles_y;
     };
     // window slots / barriers alternate (a = this group, b = next group); vertical-tap slots rotate through four
+    constexpr unsigned WIN_BYTES = CC == 3 ? V3_WIN_BYTES : V3_WIN_BYTES / 4;   // 4 rows x 60 pixels x (16 | 4) bytes
+    constexpr unsigned PIX = CC == 3 ? 16u : 4u;
     unsigned w_a = base, w_b = base + V3_WIN_BYTES, b_a = bar0, b_b = bar0 + 8, p_a = 0, p_b = 0, p_h = 0;
     unsigned v_c = base + F3_OFF_V, v_n = v_c + F3_V_BYTES, v_f = v_c + 2 * F3_V_BYTES, v_p = v_c + 3 * F3_V_BYTES;
     // v_c: this group, v_n: next group (in flight), v_f: free -> receives group + 2 at the end of this group... see end_group
     auto issue_group = [&](unsigned wslot, unsigned vslot, unsigned bar, int b, int y0, int x0, int gi) {
         if (lead) {
-            mbar_expect_tx_a(bar, V3_WIN_BYTES + F3_V_BYTES);
-            tma_load_3d_a(wslot, &map_in, bar, 4 * x0, y0 + V3_GROUP * gi, b, pol_keep);
-            tma_load_4d_a(vslot, &map_v, bar, x0, y0, V3_GROUP * gi, b, pol_once);
+            // tiled: planes 4gi .. 4gi+3 of this warp tile are contiguous (256 bytes each); planes past the 51st do not exist
+            // (nothing reads them: rows with fy > 50 are masked at compile time)
+            const int nplanes = TILED ? max(0, min(V3_GROUP, K51 - V3_GROUP * gi)) : V3_GROUP;
+            mbar_expect_tx_a(bar, WIN_BYTES + (unsigned)nplanes * (F3_V_BYTES / V3_GROUP));
+            tma_load_3d_a(wslot, &map_in, bar, (CC == 3 ? 4 : 1) * x0, y0 + V3_GROUP * gi, b, pol_keep);
+            if (!TILED) tma_load_4d_a(vslot, &map_v, bar, x0, y0, V3_GROUP * gi, b, pol_once);
+            else if (nplanes > 0) {
+                const float* src = tl.v + (((int64_t)b * tl.tiles_y8 + y0 / F3_R) * tl.tiles_x8 + x0 / V3_COLS) * (K51 * 64) + gi * (V3_GROUP * 64);
+                bulk_load_a(vslot, src, (unsigned)nplanes * (F3_V_BYTES / V3_GROUP), bar);
+            }
         }
     };
     auto issue_h = [&](int b, int y0, int x0) {
         if (lead) {
             mbar_expect_tx_a(hbar, F3_H_BYTES);
-            tma_load_4d_a(base + F3_OFF_H, &map_h, hbar, x0, y0, 0, b, pol_once);
+            if (!TILED) tma_load_4d_a(base + F3_OFF_H, &map_h, hbar, x0, y0, 0, b, pol_once);
+            else bulk_load_a(base + F3_OFF_H, tl.h + (((int64_t)b * tl.tiles_y8 + y0 / F3_R) * tl.tiles_x8 + x0 / V3_COLS) * (K51 * 64),
+                             F3_H_BYTES, hbar);
         }
     };
 
@@ -481,7 +510,7 @@ sepconv_fwd_k51_v3_kernel(const __grid_constant__ CUtensorMap map_in, const __gr
     issue_group(w_a, v_c, b_a, tb, ty0, tx0, 0);
     issue_group(w_b, v_n, b_b, tb, ty0, tx0, 1);
 
-    const unsigned lane_win = (unsigned)(pg + g) * 16u;
+    const unsigned lane_win = (unsigned)(pg + g) * PIX;
     const unsigned lane_v = (unsigned)pg * 4u;
 
 #pragma unroll 1
@@ -491,7 +520,7 @@ sepconv_fwd_k51_v3_kernel(const __grid_constant__ CUtensorMap map_in, const __gr
         if (has_next) decode(ntile, nb, ny0, nx0);
         if (has_next && warp == 0 && lead) s_ticket[tile_no & 1] = atomicAdd(next_tile_counter, 1);
 
-        float2 h2[NP][NT], acc[3][NP];
+        float2 h2[NP][NT], acc[CC][NP];
         mbar_wait_a(hbar, p_h);
         p_h ^= 1;
         {
@@ -505,7 +534,7 @@ sepconv_fwd_k51_v3_kernel(const __grid_constant__ CUtensorMap map_in, const __gr
             }
         }
 #pragma unroll
-        for (int c = 0; c < 3; ++c)
+        for (int c = 0; c < CC; ++c)
 #pragma unroll
             for (int pp = 0; pp < NP; ++pp) acc[c][pp] = make_float2(0.f, 0.f);
         __syncwarp();
@@ -523,7 +552,7 @@ sepconv_fwd_k51_v3_kernel(const __grid_constant__ CUtensorMap map_in, const __gr
                 const int pl = d >= 0 ? d : (d >= -4 ? d + 4 : d + 8);
                 va[p] = slot + (pl * R + p) * V3_COLS * 4;
             }
-            fwd3_step<S>(wa + U * V3_WIN_COLS * 16, va, novalid, h2, acc);
+            fwd3_step<S, CC>(wa + U * V3_WIN_COLS * PIX, va, novalid, h2, acc);
         };
         auto run_group = [&](auto gi_tag) {
             mbar_wait_a(b_a, p_a);
@@ -565,7 +594,7 @@ sepconv_fwd_k51_v3_kernel(const __grid_constant__ CUtensorMap map_in, const __gr
         // ---- sum the 4 tap groups of each pixel: lane g ends up with rows 2g, 2g+1 of every channel
         const int x = tx0 + pg;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
+        for (int c = 0; c < CC; ++c) {
             float val[R];
 #pragma unroll
             for (int pp = 0; pp < NP; ++pp) { val[2 * pp] = acc[c][pp].x; val[2 * pp + 1] = acc[c][pp].y; }
@@ -575,7 +604,11 @@ sepconv_fwd_k51_v3_kernel(const __grid_constant__ CUtensorMap map_in, const __gr
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
                     const int p = 2 * g + j;
-                    if (ty0 + p < sh.H) ob[(int64_t)p * sh.W] = val[j];
+                    if (ty0 + p < sh.H) {
+                        ob[(int64_t)p * sh.W] = val[j];
+                        // gray x3 shortcut: the input planes are identical copies, so are the outputs
+                        for (int rc = 1; rc < replicas; ++rc) ob[(int64_t)rc * plane + (int64_t)p * sh.W] = val[j];
+                    }
                 }
             }
         }

@@ -278,3 +278,50 @@ class ModuleInterpolationTail(torch.nn.Module):
 
     def forward(self, i1, i2, k1v, k1h, k2v, k2h):
         return _InterpolationTail.apply(i1, i2, k1v, k1h, k2v, k2h)
+
+
+# ---------------------------------------------------------------------------------------------
+# Tile-major taps (SURVEY.md section 8f, N2)
+# ---------------------------------------------------------------------------------------------
+def taps_to_tiled(taps: torch.Tensor) -> torch.Tensor:
+    """[B,51,H,W] taps -> the tile-major layout ``[B, ceil(H/8), ceil(W/8), 51, 8, 8]`` (zeros outside the image) that
+    :func:`sepconv_forward_tiled` consumes: all 51 taps of an 8x8 pixel tile are 13 KB of contiguous memory.  This is
+    the layout a tap producer -- the last ``Conv2d(51,51,3)`` of ``IFNet._kernel_module``,
+    sff_scripts_interp/model/model_interp.py:129-137 -- should write; the conversion exists for producers that cannot
+    (and for the parity tests)."""
+    if taps.is_cuda == False:
+        raise NotImplementedError()
+    if taps.dtype != torch.float32 or taps.dim() != 4 or taps.size(1) != 51:
+        raise TypeError("taps_to_tiled: float32 [B,51,H,W] required")
+    taps = taps.contiguous()
+    B, _, H, W = taps.shape
+    out = torch.empty((B, (H + 7) // 8, (W + 7) // 8, 51, 8, 8), dtype=torch.float32, device=taps.device)
+    if out.numel():
+        code = _lib.load().sstem_taps_to_tiled(taps.data_ptr(), out.data_ptr(), B, H, W, _stream_ptr(taps))
+        if code:
+            _lib.check(code, "sstem_taps_to_tiled")
+    return out
+
+
+def sepconv_forward_tiled(input: torch.Tensor, vertical_tiled: torch.Tensor, horizontal_tiled: torch.Tensor) -> torch.Tensor:
+    """``SeparableConvolution.apply(input, vertical, horizontal)`` with both tap tensors in the tile-major layout of
+    :func:`taps_to_tiled`; forward only; bit-identical to the [B,51,H,W] path.  Follows :func:`set_gray_replicated`."""
+    for t in (input, vertical_tiled, horizontal_tiled):
+        if t.is_cuda == False:
+            raise NotImplementedError()
+        if t.dtype != torch.float32:
+            raise TypeError("sepconv_forward_tiled: float32 tensors required")
+    assert (input.is_contiguous() == True) and (vertical_tiled.is_contiguous() == True) and (horizontal_tiled.is_contiguous() == True)
+    B, C, IH, IW = input.shape
+    H, W = IH - 50, IW - 50
+    want = (B, (H + 7) // 8, (W + 7) // 8, 51, 8, 8)
+    assert tuple(vertical_tiled.shape) == want and tuple(horizontal_tiled.shape) == want, f"tiled taps must be {want}"
+    out = torch.empty((B, C, H, W), dtype=torch.float32, device=input.device)
+    if out.numel():
+        gray = _is_gray(input)
+        code = _lib.load().sstem_sepconv_forward_tiled(input.data_ptr(), vertical_tiled.data_ptr(), horizontal_tiled.data_ptr(),
+                                                       out.data_ptr(), B, C, H, W, 51, _lib.SEPCONV_GRAY_REPLICATED if gray else 0,
+                                                       _stream_ptr(input))
+        if code:
+            _lib.check(code, "sstem_sepconv_forward_tiled")
+    return out

@@ -53,6 +53,18 @@ def main():
             print(json.dumps({"op": "bwd_taps", "shape": [B, C, H, W], "ms": round(ms, 4), "gpix_s": round(px / ms / 1e6, 3),
                               "tflops_alg": round(fl / ms / 1e9, 2), "frac_probe": round(fl / ms / 1e9 / peak, 3)}))
             del gv, gh
+        if "tiled" in what:
+            vt, ht = pkg.taps_to_tiled(v), pkg.taps_to_tiled(h)
+            for flag, nm in ((0, "fwd_tiled"), (2, "fwd_tiled_gray")):
+                if flag and C != 3:
+                    continue
+                if flag:
+                    inp[:, 1:] = inp[:, :1]
+                ms = timeit(lambda: lib.sstem_sepconv_forward_tiled(inp.data_ptr(), vt.data_ptr(), ht.data_ptr(), out.data_ptr(), B, C, H, W, K, flag, st))
+                ms0 = timeit(lambda: lib.sstem_sepconv_forward(inp.data_ptr(), v.data_ptr(), h.data_ptr(), out.data_ptr(), B, C, H, W, K, flag, st))
+                print(json.dumps({"op": nm, "shape": [B, C, H, W], "ms_tiled": round(ms, 4), "ms_nchw": round(ms0, 4),
+                                  "gpix_s_tiled": round(px / ms / 1e6, 3), "tap_GBs_tiled": round(px * 408 / ms / 1e6, 1), "tap_GBs_nchw": round(px * 408 / ms0 / 1e6, 1)}))
+            del vt, ht
         if "gray" in what and C == 3:
             gv, gh = torch.empty_like(v), torch.empty_like(h)
             inp[:, 1:] = inp[:, :1]
