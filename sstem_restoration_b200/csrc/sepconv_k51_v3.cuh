@@ -17,8 +17,8 @@
 //     boxes issued right after the current tile copied its own into registers, a whole tile (~30 us) ahead.
 //
 // Per step a lane issues 130 FFMA2, 13 LDS.128 (window), 4 LDS (v), the gv transpose-reduce and one store; the
-// ring costs ~10 instructions per 4 steps.  Arithmetic (operation order) is that of generations 1 and 2: results
-// are bit-identical.
+// ring costs ~10 instructions per 4 steps.  The forward's operation order is that of generation 1 (bit-identical
+// results); grad_vertical sums its 13 tap terms in one chain instead of two (same tolerance against the oracle).
 #pragma once
 #include "sepconv_k51_v2.cuh"
 #include <type_traits>
@@ -104,6 +104,10 @@ __device__ __forceinline__ float4 lds_f32x4(unsigned addr) {
     return v;
 }
 
+#ifndef SSTEM_BWD3_SPLIT
+#define SSTEM_BWD3_SPLIT 0                                 // 1: two gv partial sums per row pair (generation 1's operation order);
+                                                           // one chain measured 0.8 % faster here (4 fewer FADD per step)
+#endif
 // One input row; same arithmetic as bwd2_step, operands addressed by shared-memory byte addresses:
 //   pa            window row of this step, already offset to the lane's first tap column
 //   va[p]         address of v[fy = s - p][row p][column of the lane]   (only read when the row is active)
@@ -156,12 +160,13 @@ __device__ __forceinline__ void bwd3_step(unsigned pa, const unsigned (&va)[4], 
             }
             if (WH) gh2[pp][t] = __ffma2_rn(t2[t][pp], v2[pp], gh2[pp][t]);
             if (WV) {
-                if (t & 1) gvb[pp] = __ffma2_rn(t2[t][pp], h2[pp][t], gvb[pp]);
+                if (SSTEM_BWD3_SPLIT && (t & 1)) gvb[pp] = __ffma2_rn(t2[t][pp], h2[pp][t], gvb[pp]);
                 else gva[pp] = __ffma2_rn(t2[t][pp], h2[pp][t], gva[pp]);
             }
         }
 #pragma unroll
-    for (int pp = 0; pp < NP; ++pp) gvp[pp] = make_float2(gva[pp].x + gvb[pp].x, gva[pp].y + gvb[pp].y);
+    for (int pp = 0; pp < NP; ++pp)
+        gvp[pp] = SSTEM_BWD3_SPLIT ? make_float2(gva[pp].x + gvb[pp].x, gva[pp].y + gvb[pp].y) : gva[pp];
 }
 
 template <bool WV, bool WH, bool ACCUM>
