@@ -98,12 +98,23 @@ __device__ __forceinline__ float lds_f32(unsigned addr) {
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
     return v;
 }
+// Ordered variant for the tile-start copies of the tap / gradient buffers: the "memory" clobber keeps the compiler from
+// sinking the load below the TMA request that refills the buffer (it did: the values are first used deep inside the
+// first step, and 5 pixels in 500 000 came out wrong).
+__device__ __forceinline__ float lds_f32_ordered(unsigned addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ float4 lds_f32x4(unsigned addr) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     return v;
 }
 
+#ifndef SSTEM_V3_REREAD
+#define SSTEM_V3_REREAD 1
+#endif
 #ifndef SSTEM_BWD3_SPLIT
 #define SSTEM_BWD3_SPLIT 0                                 // 1: two gv partial sums per row pair (generation 1's operation order);
                                                            // one chain measured 0.8 % faster here (4 fewer FADD per step)
@@ -112,7 +123,7 @@ __device__ __forceinline__ float4 lds_f32x4(unsigned addr) {
 //   pa            window row of this step, already offset to the lane's first tap column
 //   va[p]         address of v[fy = s - p][row p][column of the lane]   (only read when the row is active)
 template <int S, bool WV, bool WH>
-__device__ __forceinline__ void bwd3_step(unsigned pa, const unsigned (&va)[4], bool novalid,
+__device__ __forceinline__ void bwd3_step(unsigned pa, unsigned pa_last, const unsigned (&va)[4],
                                           const float2 (&g2)[3][2], const float2 (&h2)[2][13],
                                           float2 (&gh2)[2][13], float2 (&gvp)[2]) {
     constexpr int NP = 2, NT = 13;
@@ -131,14 +142,8 @@ __device__ __forceinline__ void bwd3_step(unsigned pa, const unsigned (&va)[4], 
     float2 t2[NT][NP];
     float4 P[NT];
 #pragma unroll
-    for (int t = 0; t < NT; ++t) {
-        P[t] = lds_f32x4(pa + 64 * t);                     // channels x, y, z of column x + g + 4t
-        if (t == NT - 1) {                                 // tap 51 does not exist (lanes g == 3)
-            P[t].x = novalid ? 0.f : P[t].x;
-            P[t].y = novalid ? 0.f : P[t].y;
-            P[t].z = novalid ? 0.f : P[t].z;
-        }
-    }
+    for (int t = 0; t < NT; ++t)                           // channels x, y, z of column x + g + 4t; slot 12 of the lanes
+        P[t] = lds_f32x4(t == NT - 1 ? pa_last : pa + 64 * t);   // g == 3 (tap 51 does not exist) rereads tap 47, h = 0 there
 #pragma unroll
     for (int c = 0; c < 3; ++c)
 #pragma unroll
@@ -249,6 +254,7 @@ sepconv_bwd_taps_k51_v3_kernel(const __grid_constant__ CUtensorMap map_in, const
     issue_group(s_nxt, b_nxt, tb, ty0, tx0, 1);
 
     const unsigned lane_win = (unsigned)(pg + g) * 16u;    // lane's first tap column inside a window row
+    const unsigned lane_last = lane_win + ((novalid && SSTEM_V3_REREAD) ? 11u : 12u) * 64u;   // its slot 12 (g == 3: tap 47 again, see the h copy)
     const unsigned lane_v = V3_WIN_BYTES + (unsigned)pg * 4u;
 
 #pragma unroll 1
@@ -270,9 +276,12 @@ sepconv_bwd_taps_k51_v3_kernel(const __grid_constant__ CUtensorMap map_in, const
 #pragma unroll
                 for (int pp = 0; pp < NP; ++pp) {
                     gh2[pp][t] = make_float2(0.f, 0.f);
-                    h2[pp][t] = WV ? make_float2(lds_f32(ha + ((tap * R + 2 * pp) * V3_COLS) * 4),
-                                                 lds_f32(ha + ((tap * R + 2 * pp + 1) * V3_COLS) * 4))
+                    h2[pp][t] = WV ? make_float2(lds_f32_ordered(ha + ((tap * R + 2 * pp) * V3_COLS) * 4),
+                                                 lds_f32_ordered(ha + ((tap * R + 2 * pp + 1) * V3_COLS) * 4))
                                    : make_float2(0.f, 0.f);
+                    // tap 51 does not exist: its window value is tap 47's (finite whenever the lane's own taps are), its weight 0,
+                    // its gh accumulator is never stored
+                    if (t == NT - 1 && novalid) h2[pp][t] = make_float2(0.f, 0.f);
                 }
             }
             const unsigned ga = base + V3_OFF_G + (unsigned)pg * 4u;
@@ -280,10 +289,12 @@ sepconv_bwd_taps_k51_v3_kernel(const __grid_constant__ CUtensorMap map_in, const
             for (int c = 0; c < 3; ++c)
 #pragma unroll
                 for (int pp = 0; pp < NP; ++pp)
-                    g2[c][pp] = make_float2(lds_f32(ga + ((c * R + 2 * pp) * V3_COLS) * 4), lds_f32(ga + ((c * R + 2 * pp + 1) * V3_COLS) * 4));
+                    g2[c][pp] = make_float2(lds_f32_ordered(ga + ((c * R + 2 * pp) * V3_COLS) * 4), lds_f32_ordered(ga + ((c * R + 2 * pp + 1) * V3_COLS) * 4));
         }
-        __syncwarp();                                      // every lane has its copy: the buffers may be refilled
-        if (has_next) issue_hg(nb, ny0, nx0);
+        // The two buffers are refilled (next tile's taps) only after the first group below: they may be overwritten once
+        // every lane's copy has ARRIVED in registers, not merely been issued -- the 64 loads queue behind the other warps'
+        // shared-memory traffic, and a TMA write issued right here overtook them now and then (grad_vertical wrong in
+        // ~5 of 500 000 pixels, differently from run to run).  After group 0 every copied value has been an FFMA2 operand.
 
         const int x = tx0 + pg;
         const bool col_ok = x < sh.W;
@@ -303,7 +314,7 @@ sepconv_bwd_taps_k51_v3_kernel(const __grid_constant__ CUtensorMap map_in, const
         };
         // One group of 4 input rows.  GI >= 0: compile-time group index (first / last groups of the tile, whose steps
         // are partially active); GI < 0: steady state, runtime group index gi.
-        auto run_step = [&](auto gi_tag, auto u_tag, int gi, unsigned wa, unsigned vc, unsigned vp) {
+        auto run_step = [&](auto gi_tag, auto u_tag, int gi, unsigned wa, unsigned wl, unsigned vc, unsigned vp) {
             constexpr int GI = decltype(gi_tag)::value, U = decltype(u_tag)::value;
             constexpr int S = GI < 0 ? -1 : GI * V3_GROUP + U;            // compile-time step of the partial groups
             if (GI >= 0 && GI * V3_GROUP + U >= V2_WIN_H) return;         // rows 54, 55 of the last group: nothing to do
@@ -311,17 +322,17 @@ sepconv_bwd_taps_k51_v3_kernel(const __grid_constant__ CUtensorMap map_in, const
 #pragma unroll
             for (int p = 0; p < 4; ++p)                    // plane s - p: this group's slot or the previous one's
                 va[p] = (U - p >= 0 ? vc + ((U - p) * R + p) * V3_COLS * 4 : vp + ((V3_GROUP + U - p) * R + p) * V3_COLS * 4);
-            bwd3_step<S, WV, WH>(wa + U * V3_WIN_COLS * 16, va, novalid, g2, h2, gh2, gvp);
+            bwd3_step<S, WV, WH>(wa + U * V3_WIN_COLS * 16, wl + U * V3_WIN_COLS * 16, va, g2, h2, gh2, gvp);
             store_gv(V3_GROUP * gi + U - g);
         };
         auto run_group = [&](auto gi_tag, int gi) {
             mbar_wait_a(b_cur, p_cur);
             p_cur ^= 1;
-            const unsigned wa = s_cur + lane_win, vc = s_cur + lane_v, vp = s_prv + lane_v;
-            run_step(gi_tag, std::integral_constant<int, 0>{}, gi, wa, vc, vp);
-            run_step(gi_tag, std::integral_constant<int, 1>{}, gi, wa, vc, vp);
-            run_step(gi_tag, std::integral_constant<int, 2>{}, gi, wa, vc, vp);
-            run_step(gi_tag, std::integral_constant<int, 3>{}, gi, wa, vc, vp);
+            const unsigned wa = s_cur + lane_win, wl = s_cur + lane_last, vc = s_cur + lane_v, vp = s_prv + lane_v;
+            run_step(gi_tag, std::integral_constant<int, 0>{}, gi, wa, wl, vc, vp);
+            run_step(gi_tag, std::integral_constant<int, 1>{}, gi, wa, wl, vc, vp);
+            run_step(gi_tag, std::integral_constant<int, 2>{}, gi, wa, wl, vc, vp);
+            run_step(gi_tag, std::integral_constant<int, 3>{}, gi, wa, wl, vc, vp);
         };
         auto end_group = [&](bool next_tile, int gi_issue) {   // everyone is done with the previous group's slot: refill it
             __syncwarp();
@@ -332,6 +343,7 @@ sepconv_bwd_taps_k51_v3_kernel(const __grid_constant__ CUtensorMap map_in, const
 
         run_group(std::integral_constant<int, 0>{}, 0);
         end_group(false, 2);
+        if (has_next) issue_hg(nb, ny0, nx0);              // see above: h2 / g2 are in registers for sure by now
 #pragma unroll 1
         for (int gi = 1; gi < 12; ++gi) {                  // groups 1..11 = steps 4..47: every row active
             run_group(std::integral_constant<int, -1>{}, gi);
@@ -385,7 +397,7 @@ constexpr unsigned F3_WARP_BYTES = F3_OFF_BAR + 128;             // 24960 = 195 
 constexpr size_t F3_SMEM = (size_t)V3_WARPS * F3_WARP_BYTES + 128;
 
 template <int S, int CC>
-__device__ __forceinline__ void fwd3_step(unsigned pa, const unsigned (&va)[8], bool novalid,
+__device__ __forceinline__ void fwd3_step(unsigned pa, unsigned pa_last, const unsigned (&va)[8],
                                           const float2 (&h2)[4][13], float2 (&acc)[CC][4]) {
     constexpr int NP = 4, NT = 13;
     float2 v2[NP];
@@ -400,13 +412,10 @@ __device__ __forceinline__ void fwd3_step(unsigned pa, const unsigned (&va)[8], 
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
         float4 P;                                          // CC == 3: channel-interleaved window, one LDS.128 per tap;
-        if (CC == 3) P = lds_f32x4(pa + 64 * t);           // CC == 1: planar window, one LDS.32
-        else P = make_float4(lds_f32(pa + 16 * t), 0.f, 0.f, 0.f);
-        if (t == NT - 1) {                                 // tap 51 does not exist (lanes g == 3)
-            P.x = novalid ? 0.f : P.x;
-            P.y = novalid ? 0.f : P.y;
-            P.z = novalid ? 0.f : P.z;
-        }
+        // slot 12 of the lanes g == 3 (tap 51 does not exist) rereads tap 47's column; h is 0 there
+        const unsigned a = t == NT - 1 ? pa_last : pa + (CC == 3 ? 64 : 16) * t;
+        if (CC == 3) P = lds_f32x4(a);                     // CC == 1: planar window, one LDS.32
+        else P = make_float4(lds_f32(a), 0.f, 0.f, 0.f);
 #pragma unroll
         for (int c = 0; c < CC; ++c) {
             const float p = c == 0 ? P.x : (c == 1 ? P.y : P.z);
@@ -516,6 +525,7 @@ sepconv_fwd_k51_v3_kernel(const __grid_constant__ CUtensorMap map_in, const __gr
     issue_group(w_b, v_n, b_b, tb, ty0, tx0, 1);
 
     const unsigned lane_win = (unsigned)(pg + g) * PIX;
+    const unsigned lane_last = lane_win + (novalid ? 11u : 12u) * 4u * PIX;
     const unsigned lane_v = (unsigned)pg * 4u;
 
 #pragma unroll 1
@@ -534,18 +544,19 @@ sepconv_fwd_k51_v3_kernel(const __grid_constant__ CUtensorMap map_in, const __gr
             for (int t = 0; t < NT; ++t) {
                 const int tap = (t == NT - 1 && novalid) ? (G * (NT - 2) + g) : (G * t + g);
 #pragma unroll
-                for (int pp = 0; pp < NP; ++pp)
-                    h2[pp][t] = make_float2(lds_f32(ha + ((tap * R + 2 * pp) * V3_COLS) * 4), lds_f32(ha + ((tap * R + 2 * pp + 1) * V3_COLS) * 4));
+                for (int pp = 0; pp < NP; ++pp) {
+                    h2[pp][t] = make_float2(lds_f32_ordered(ha + ((tap * R + 2 * pp) * V3_COLS) * 4), lds_f32_ordered(ha + ((tap * R + 2 * pp + 1) * V3_COLS) * 4));
+                    if (t == NT - 1 && novalid) h2[pp][t] = make_float2(0.f, 0.f);   // tap 51 does not exist: weight 0 on tap 47's column
+                }
             }
         }
 #pragma unroll
         for (int c = 0; c < CC; ++c)
 #pragma unroll
             for (int pp = 0; pp < NP; ++pp) acc[c][pp] = make_float2(0.f, 0.f);
-        __syncwarp();
-        if (has_next) issue_h(nb, ny0, nx0);
+        // (the tap buffer is refilled after the second group: see the tap-gradient kernel)
 
-        auto run_step = [&](auto gi_tag, auto u_tag, unsigned wa, unsigned vc, unsigned vp1, unsigned vp2) {
+        auto run_step = [&](auto gi_tag, auto u_tag, unsigned wa, unsigned wl, unsigned vc, unsigned vp1, unsigned vp2) {
             constexpr int GI = decltype(gi_tag)::value, U = decltype(u_tag)::value;
             constexpr int S = GI < 0 ? -1 : GI * V3_GROUP + U;
             if (GI >= 0 && GI * V3_GROUP + U >= F3_ROWS) return;          // rows 58, 59 of the last group
@@ -557,16 +568,16 @@ sepconv_fwd_k51_v3_kernel(const __grid_constant__ CUtensorMap map_in, const __gr
                 const int pl = d >= 0 ? d : (d >= -4 ? d + 4 : d + 8);
                 va[p] = slot + (pl * R + p) * V3_COLS * 4;
             }
-            fwd3_step<S, CC>(wa + U * V3_WIN_COLS * PIX, va, novalid, h2, acc);
+            fwd3_step<S, CC>(wa + U * V3_WIN_COLS * PIX, wl + U * V3_WIN_COLS * PIX, va, h2, acc);
         };
         auto run_group = [&](auto gi_tag) {
             mbar_wait_a(b_a, p_a);
             p_a ^= 1;
-            const unsigned wa = w_a + lane_win, vc = v_c + lane_v, vp1 = v_p1 + lane_v, vp2 = v_p2 + lane_v;
-            run_step(gi_tag, std::integral_constant<int, 0>{}, wa, vc, vp1, vp2);
-            run_step(gi_tag, std::integral_constant<int, 1>{}, wa, vc, vp1, vp2);
-            run_step(gi_tag, std::integral_constant<int, 2>{}, wa, vc, vp1, vp2);
-            run_step(gi_tag, std::integral_constant<int, 3>{}, wa, vc, vp1, vp2);
+            const unsigned wa = w_a + lane_win, wl = w_a + lane_last, vc = v_c + lane_v, vp1 = v_p1 + lane_v, vp2 = v_p2 + lane_v;
+            run_step(gi_tag, std::integral_constant<int, 0>{}, wa, wl, vc, vp1, vp2);
+            run_step(gi_tag, std::integral_constant<int, 1>{}, wa, wl, vc, vp1, vp2);
+            run_step(gi_tag, std::integral_constant<int, 2>{}, wa, wl, vc, vp1, vp2);
+            run_step(gi_tag, std::integral_constant<int, 3>{}, wa, wl, vc, vp1, vp2);
         };
         // end of group i: its window slot and the vertical-tap slot of group i-2 are free -> they receive group i+2
         auto end_group = [&](bool next_tile, int gi_issue) {
@@ -584,6 +595,7 @@ sepconv_fwd_k51_v3_kernel(const __grid_constant__ CUtensorMap map_in, const __gr
         end_group(false, 2);
         run_group(std::integral_constant<int, 1>{});
         end_group(false, 3);
+        if (has_next) issue_h(nb, ny0, nx0);               // all 8 rows have used their taps by step 7
 #pragma unroll 1
         for (int gi = 2; gi < 12; ++gi) {                  // groups 2..11 = steps 8..47: every row active
             run_group(std::integral_constant<int, -1>{});
