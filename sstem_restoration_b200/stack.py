@@ -105,7 +105,7 @@ def restore_stack(stack: torch.Tensor, taps_fn: Callable, flow_fn: Optional[Call
         interp = prediction_to_uint8(interpolation_tail(x[:, :3], x[:, 3:6], k1v, k1h, k2v, k2h))
         if flow_fn:                                                  # the correction module's flow net (out of scope)
             xk = sections_to_input(stack[k])                         # [1,3,H,W]: input_sff
-            warped = SpatialTransformation()(xk, flow_fn(k, xk, interp))   # flow [1,H,W,2], any strides
+            warped = SpatialTransformation()(xk[:, :1], flow_fn(k, xk, interp))   # flow [1,H,W,2], any strides; planes identical
             warped_gray, stitch = warp_stitch(warped, interp)
 
     Returns a dict of uint8 tensors -- ``interp`` and, with ``flow_fn``, ``warped`` and ``stitch`` -- plus ``stats``.
@@ -152,7 +152,9 @@ def restore_stack(stack: torch.Tensor, taps_fn: Callable, flow_fn: Optional[Call
             interp = prediction_to_uint8(interpolation_tail(x[:, :3], x[:, 3:6], k1v, k1h, k2v, k2h), 0, out=local["interp"][i:i + 1])
             if flow_fn is not None:
                 xk = sections_to_input(cache.get(k), None, 0)
-                warped = warp(xk, flow_fn(k, xk, interp))
+                # input_sff is a gray section replicated x3 (inference.py:129-131): its three warped planes are identical and
+                # PIL's 'L' of an R = G = B triple is R, so one plane is warped and stitched (a third of the bytes, same bits)
+                warped = warp(xk[:, :1], flow_fn(k, xk, interp))
                 warp_stitch(warped, interp, out=(local["warped"][i:i + 1], local["stitch"][i:i + 1]))
             if to_host:
                 done = torch.cuda.Event()

@@ -21,6 +21,11 @@ if op == "warp":
     kind = os.environ.get("FLOW", "noise")
     if kind == "noise":
         fl = (5 * torch.randn((B, 2, H, W), device=dev)).permute(0, 2, 3, 1)
+    elif kind == "fold":                                 # the SFF fold flow of the benchmark (gen_flow, seed 555)
+        import numpy as np
+        from sstem_restoration_b200 import synth
+        f = synth.random_fold_flow(H, W, 555)[0]
+        fl = torch.from_numpy(np.ascontiguousarray(f.transpose(2, 0, 1))[None]).to(dev).expand(B, 2, H, W).contiguous().permute(0, 2, 3, 1)
     else:
         fl = (torch.zeros((B, 2, H, W), device=dev) + 3.3).permute(0, 2, 3, 1)
     m = pkg.SpatialTransformation(True)
