@@ -273,6 +273,24 @@ int sstem_sepconv_forward_tiled(const float* input, const float* vertical_tiled,
                                 int32_t K, uint32_t flags, void* stream);
 
 /*
+ * Gray x3 detection on the device, without a host round trip.  Every reference caller feeds sepconv a grayscale section
+ * replicated x3 (sff_scripts_interp/data/data_provider.py:136-137, inference.py:71-77): identical channel planes, for which
+ * one plane of work gives all outputs (SSTEM_SEPCONV_GRAY_REPLICATED).  These entry points decide that themselves:
+ * forward_detect compares the planes with a streaming kernel, writes *gray_flag (DEVICE int32: non-zero = identical planes) and
+ * launches BOTH paths, each gated on the flag -- the one that does not apply returns at its first instruction (~3 us);
+ * backward_detect reads the flag the forward left.  Results equal those of sstem_sepconv_forward / _backward with the flag
+ * set by hand (forward: bit-identical to the general path).  K != 51, C == 1 or STRICT_ORDER: plain general path, flag 0.
+ */
+int sstem_sepconv_forward_detect(const float* input, const float* vertical, const float* horizontal,
+                                 float* output, int64_t B, int64_t C, int64_t H, int64_t W,
+                                 int32_t K, uint32_t flags, int32_t* gray_flag, void* stream);
+int sstem_sepconv_backward_detect(const float* grad_output, const float* input,
+                                  const float* vertical, const float* horizontal,
+                                  float* grad_input, float* grad_vertical, float* grad_horizontal,
+                                  int64_t B, int64_t C, int64_t H, int64_t W,
+                                  int32_t K, uint32_t flags, const int32_t* gray_flag, void* stream);
+
+/*
  * FP32 FMA-pipe probe: runs a register-resident FFMA loop on every SM of the
  * current device and returns the sustained rate in TFLOP/s (2 flop per FMA).
  * bench.py uses it as the measured denominator of the sepconv roofline

@@ -39,6 +39,7 @@ EXPORTED_SYMBOLS = (
     "sstem_warp_forward", "sstem_image_warp", "sstem_sff_degrade", "sstem_sff_contrast",
     "sstem_sections_to_input", "sstem_prediction_to_u8", "sstem_warp_stitch_u8",
     "sstem_taps_tiled_elems", "sstem_taps_to_tiled", "sstem_sepconv_forward_tiled",
+    "sstem_sepconv_forward_detect", "sstem_sepconv_backward_detect",
     "sstem_fp32_peak_probe", "sstem_launch_count", "sstem_abi_version", "sstem_error_string",
 )
 
@@ -91,6 +92,10 @@ def load() -> ctypes.CDLL:
         lib.sstem_taps_to_tiled.restype = ctypes.c_int
         lib.sstem_sepconv_forward_tiled.argtypes = [_c_p, _c_p, _c_p, _c_p, _c_i64, _c_i64, _c_i64, _c_i64, _c_i32, _c_u32, _c_p]
         lib.sstem_sepconv_forward_tiled.restype = ctypes.c_int
+        lib.sstem_sepconv_forward_detect.argtypes = [_c_p, _c_p, _c_p, _c_p, _c_i64, _c_i64, _c_i64, _c_i64, _c_i32, _c_u32, _c_p, _c_p]
+        lib.sstem_sepconv_forward_detect.restype = ctypes.c_int
+        lib.sstem_sepconv_backward_detect.argtypes = [_c_p] * 7 + [_c_i64] * 4 + [_c_i32, _c_u32, _c_p, _c_p]
+        lib.sstem_sepconv_backward_detect.restype = ctypes.c_int
         lib.sstem_fp32_peak_probe.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
         lib.sstem_fp32_peak_probe.restype = ctypes.c_int
         lib.sstem_launch_count.argtypes = []

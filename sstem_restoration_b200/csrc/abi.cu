@@ -5,6 +5,7 @@
 
 namespace sstem {
 std::atomic<int64_t> g_launches{0};
+thread_local LaunchGate g_gate;
 }
 using namespace sstem;
 
@@ -62,6 +63,62 @@ extern "C" int sstem_sepconv_backward(const float* grad_output, const float* inp
         else e = launch_sepconv_bwd_input_generic(grad_output, vertical, horizontal, grad_input, B, C, H, W, K, s);
     }
     return e;
+}
+
+// ---- gray x3 detection on the device (no host round trip) ------------------------------------------------------------
+namespace sstem {
+int launch_planes_equal(const float* in, int64_t B, int64_t C, int64_t plane, int* flag, cudaStream_t s);
+}
+
+extern "C" int sstem_sepconv_forward_detect(const float* input, const float* vertical, const float* horizontal,
+                                            float* output, int64_t B, int64_t C, int64_t H, int64_t W,
+                                            int32_t K, uint32_t flags, int32_t* gray_flag, void* stream) {
+    if (!gray_flag) return SSTEM_E_NULL;
+    if (!aligned4(gray_flag)) return SSTEM_E_ALIGN;
+    if (flags & ~SSTEM_SEPCONV_STRICT_ORDER) return SSTEM_E_FLAG;      // GRAY_REPLICATED is what this call decides itself
+    const bool detect = K == 51 && !(flags & SSTEM_SEPCONV_STRICT_ORDER) && C > 1;
+    if (!detect) {                                                      // nothing to gain: general path, flag = 0
+        const int e = sstem_sepconv_forward(input, vertical, horizontal, output, B, C, H, W, K, flags, stream);
+        if (e) return e;
+        DeviceGuard guard(output);
+        return (int)cudaMemsetAsync(gray_flag, 0, sizeof(int32_t), (cudaStream_t)stream);
+    }
+    if (!input || !vertical || !horizontal || !output) return SSTEM_E_NULL;
+    if (int e = check_sepconv_dims(B, C, H, W, K)) return e;
+    {
+        DeviceGuard guard(output);
+        if (guard.err) return guard.err;
+        if (int e = launch_planes_equal(input, B, C, (H + K - 1) * (W + K - 1), gray_flag, (cudaStream_t)stream)) return e;
+    }
+    {   // identical planes: one plane computed, C written
+        GateScope gate(gray_flag, 1);
+        if (int e = sstem_sepconv_forward(input, vertical, horizontal, output, B, C, H, W, K, SSTEM_SEPCONV_GRAY_REPLICATED, stream)) return e;
+    }
+    GateScope gate(gray_flag, 0);
+    return sstem_sepconv_forward(input, vertical, horizontal, output, B, C, H, W, K, 0, stream);
+}
+
+extern "C" int sstem_sepconv_backward_detect(const float* grad_output, const float* input,
+                                             const float* vertical, const float* horizontal,
+                                             float* grad_input, float* grad_vertical, float* grad_horizontal,
+                                             int64_t B, int64_t C, int64_t H, int64_t W,
+                                             int32_t K, uint32_t flags, const int32_t* gray_flag, void* stream) {
+    if (!gray_flag) return SSTEM_E_NULL;
+    if (flags & ~SSTEM_SEPCONV_STRICT_ORDER) return SSTEM_E_FLAG;
+    const bool detect = K == 51 && C > 1 && (grad_vertical || grad_horizontal);
+    if (!detect)
+        return sstem_sepconv_backward(grad_output, input, vertical, horizontal, grad_input, grad_vertical, grad_horizontal, B, C, H, W, K, flags, stream);
+    // grad_input does not depend on the input: computed once, ungated
+    if (grad_input)
+        if (int e = sstem_sepconv_backward(grad_output, input, vertical, horizontal, grad_input, nullptr, nullptr, B, C, H, W, K, flags, stream)) return e;
+    {
+        GateScope gate(gray_flag, 1);
+        if (int e = sstem_sepconv_backward(grad_output, input, vertical, horizontal, nullptr, grad_vertical, grad_horizontal, B, C, H, W, K,
+                                           flags | SSTEM_SEPCONV_GRAY_REPLICATED, stream))
+            return e;
+    }
+    GateScope gate(gray_flag, 0);
+    return sstem_sepconv_backward(grad_output, input, vertical, horizontal, nullptr, grad_vertical, grad_horizontal, B, C, H, W, K, flags, stream);
 }
 
 static int check_tail_args(int64_t B, int64_t C, int64_t H, int64_t W, int32_t K, uint32_t flags, int64_t bstride) {

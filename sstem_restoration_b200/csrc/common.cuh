@@ -46,6 +46,22 @@ inline int sm_count() {
 
 inline int finish_launch() { return (int)cudaGetLastError(); }
 
+// Device-side launch gate (gray x3 detection without a host round trip): a kernel launched while a gate is set reads
+// `*ptr` first and returns at once unless it equals `want`.  The C-ABI *_detect entry points launch BOTH candidate paths,
+// each under its gate; the flag is written by planes_equal_kernel earlier on the same stream.  Thread-local, so replica
+// threads do not see each other's gates.
+struct LaunchGate {
+    const int* ptr = nullptr;
+    int want = 0;
+};
+extern thread_local LaunchGate g_gate;
+struct GateScope {
+    LaunchGate prev;
+    GateScope(const int* ptr, int want) : prev(g_gate) { g_gate.ptr = ptr; g_gate.want = want; }
+    ~GateScope() { g_gate = prev; }
+};
+#define SSTEM_GATE_RETURN(gate, want) do { if ((gate) != nullptr && ((*(gate) != 0) != ((want) != 0))) return; } while (0)
+
 // One bit per device ordinal: "this kernel's function attributes have been set on that device".
 // Replica threads (nn.DataParallel) race here, so the flag is atomic; setting an attribute twice is
 // harmless, skipping it is not -- ordinals >= 64 simply set it on every call.

@@ -353,7 +353,8 @@ template <int CC, int G, int R, bool VEC, bool PAIR>
 __global__ void __launch_bounds__(128, 2)
 sepconv_fwd_k51_kernel(const float* __restrict__ in, const float* __restrict__ v,
                        const float* __restrict__ h, float* __restrict__ out,
-                       int C, int c0, int H, int W, int replicas) {
+                       int C, int c0, int H, int W, int replicas, const int* gate, int gate_want) {
+    SSTEM_GATE_RETURN(gate, gate_want);
     using Gm = Geo<G, R>;
     extern __shared__ __align__(16) float tile[];      // [CC][ROWS][PITCH] + 4 warps x v ring
     const int IW = W + K51 - 1, IH = H + K51 - 1;
@@ -581,7 +582,8 @@ sepconv_bwd_taps_k51_kernel(const float* __restrict__ gout, const float* __restr
                             const float* __restrict__ v, const float* __restrict__ h,
                             float* __restrict__ gv, float* __restrict__ gh,
                             int C, int c0, int H, int W, int replicas,
-                            int64_t in_bstride, int cs, int nplanes, float gscale) {
+                            int64_t in_bstride, int cs, int nplanes, float gscale, const int* gate, int gate_want) {
+    SSTEM_GATE_RETURN(gate, gate_want);
     static_assert(!TAIL || CC == 1, "the fused tail works on one (channel-summed) plane");
     constexpr bool accumulate = ACCUM;                   // later channel chunks (C > 3) add into gv / gh
     using Gm = Geo<G, R>;

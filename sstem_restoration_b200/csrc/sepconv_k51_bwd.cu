@@ -39,11 +39,11 @@ int launch_bwd_variant(const float* g, const float* in, const float* v, const fl
         static PerDeviceOnce done_a;
         auto kern = sepconv_bwd_taps_k51_kernel<CC, G, R, VEC, PAIR, WV, WH, true>;
         if (int e = set_smem_once(kern, smem, done_a)) return e;
-        kern<<<grid, 128, smem, s>>>(g, in, v, h, gv, gh, C, c0, H, W, replicas, (int64_t)0, 1, 1, 1.f);
+        kern<<<grid, 128, smem, s>>>(g, in, v, h, gv, gh, C, c0, H, W, replicas, (int64_t)0, 1, 1, 1.f, g_gate.ptr, g_gate.want);
     } else {
         auto kern = sepconv_bwd_taps_k51_kernel<CC, G, R, VEC, PAIR, WV, WH, false>;
         if (int e = set_smem_once(kern, smem, done)) return e;
-        kern<<<grid, 128, smem, s>>>(g, in, v, h, gv, gh, C, c0, H, W, replicas, (int64_t)0, 1, 1, 1.f);
+        kern<<<grid, 128, smem, s>>>(g, in, v, h, gv, gh, C, c0, H, W, replicas, (int64_t)0, 1, 1, 1.f, g_gate.ptr, g_gate.want);
     }
     count_launch();
     return finish_launch();

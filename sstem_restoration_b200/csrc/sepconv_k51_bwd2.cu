@@ -50,8 +50,8 @@ int launch_repack_nhwc4(const float* in, float* ws, int64_t B, int C, int c0, in
     const bool vec = (plane % 4 == 0) && aligned16(in) && ((int64_t)C * plane % 4 == 0) && ((int64_t)c0 * plane % 4 == 0);
     const int64_t work = vec ? total / 4 : total;
     const unsigned blocks = (unsigned)std::min<int64_t>((work + 255) / 256, (int64_t)sm_count() * 16);
-    if (vec) repack_nchw3_to_nhwc4_kernel<true><<<blocks, 256, 0, s>>>(in, reinterpret_cast<float4*>(ws), C, c0, plane, total);
-    else repack_nchw3_to_nhwc4_kernel<false><<<blocks, 256, 0, s>>>(in, reinterpret_cast<float4*>(ws), C, c0, plane, total);
+    if (vec) repack_nchw3_to_nhwc4_kernel<true><<<blocks, 256, 0, s>>>(in, reinterpret_cast<float4*>(ws), C, c0, plane, total, g_gate.ptr, g_gate.want);
+    else repack_nchw3_to_nhwc4_kernel<false><<<blocks, 256, 0, s>>>(in, reinterpret_cast<float4*>(ws), C, c0, plane, total, g_gate.ptr, g_gate.want);
     count_launch();
     return finish_launch();
 }
@@ -81,7 +81,7 @@ int launch_v3_kernel(const CUtensorMap& min, const CUtensorMap& mv, const CUtens
     auto kern = sepconv_bwd_taps_k51_v3_kernel<WV, WH, ACCUM>;
     if (int e = set_smem_once(kern, V3_SMEM, done)) return e;
     const int ctas = std::min<int64_t>(2 * (int64_t)sm_count(), (int64_t)sh.ntiles);
-    kern<<<ctas, V3_WARPS * 32, V3_SMEM, s>>>(min, mv, mh, mg, gv, gh, counter, sh);
+    kern<<<ctas, V3_WARPS * 32, V3_SMEM, s>>>(min, mv, mh, mg, gv, gh, counter, sh, g_gate.ptr, g_gate.want);
     count_launch();
     return finish_launch();
 }
@@ -158,7 +158,7 @@ int try_launch_bwd_taps_k51_v2(const float* g, const float* in, const float* v, 
         const int e3 = try_launch_bwd_taps_k51_v3(g, in, v, h, gv, gh, B, C, c0, H, W, accumulate, s);
         if (e3 != -1000) return e3;
     }
-    const bool off = gen != 2;                             // generation 2 is kept for A/B runs only (SSTEM_BWD_GEN=2)
+    const bool off = gen != 2 || g_gate.ptr != nullptr;    // generation 2 is kept for A/B runs only (SSTEM_BWD_GEN=2); not gated
     if (off || (W & 3) || !aligned16(v) || B > 65535 || (H + V2_R - 1) / V2_R > 65535) return -1000;
     const int64_t IH = H + K51 - 1, IW = W + K51 - 1;
     float* ws = nullptr;

@@ -13,7 +13,7 @@ int launch_fwd_variant(const float* in, const float* v, const float* h, float* o
     auto kern = sepconv_fwd_k51_kernel<CC, G, R, VEC, PAIR>;
     if (int e = set_smem_once(kern, smem, done)) return e;
     dim3 grid((unsigned)((W + Geo<G, R>::TILE_W - 1) / Geo<G, R>::TILE_W), (unsigned)((H + R - 1) / R), (unsigned)B);
-    kern<<<grid, 128, smem, s>>>(in, v, h, out, C, c0, H, W, replicas);
+    kern<<<grid, 128, smem, s>>>(in, v, h, out, C, c0, H, W, replicas, g_gate.ptr, g_gate.want);
     count_launch();
     return finish_launch();
 }

@@ -32,7 +32,7 @@ int launch_fwd_v3(const float* in, const float* v, const float* h, float* out,
     else {
         const int64_t total = B * IH * IWP;
         const unsigned blocks = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 16);
-        repack_plane_pitch_kernel<<<blocks, 256, 0, s>>>(in, ws, C, c0, (int)IH, (int)IW, (int)IWP, total);
+        repack_plane_pitch_kernel<<<blocks, 256, 0, s>>>(in, ws, C, c0, (int)IH, (int)IW, (int)IWP, total, g_gate.ptr, g_gate.want);
         count_launch();
         e = finish_launch();
     }
@@ -59,7 +59,7 @@ int launch_fwd_v3(const float* in, const float* v, const float* h, float* out,
             V3Shape sh{H, W, (int)tiles_x, (int)tiles_y, (int)(tiles_x * tiles_y * B), C, c0};
             F3Tiled tl{TILED ? v : nullptr, TILED ? h : nullptr, (int)((W + 7) / 8), (int)((H + 7) / 8)};
             const int ctas = (int)std::min<int64_t>(2 * (int64_t)sm_count(), (int64_t)sh.ntiles);
-            kern<<<ctas, V3_WARPS * 32, F3_SMEM, s>>>(min, mv, mh, tl, out, counter, sh, replicas);
+            kern<<<ctas, V3_WARPS * 32, F3_SMEM, s>>>(min, mv, mh, tl, out, counter, sh, replicas, g_gate.ptr, g_gate.want);
             count_launch();
             e = finish_launch();
         }
@@ -90,6 +90,16 @@ int try_launch_fwd_k51_v3_c1(const float* in, const float* v, const float* h, fl
     static const bool on = getenv("SSTEM_FWD_C1_GEN") && atoi(getenv("SSTEM_FWD_C1_GEN")) >= 3;
     if (!on || !fwd_gen3_enabled()) return -1000;
     return launch_fwd_v3<1, false>(in, v, h, out, B, C, c0, H, W, replicas, false, s);
+}
+
+int launch_planes_equal(const float* in, int64_t B, int64_t C, int64_t plane, int* flag, cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(flag, 1, sizeof(int), s);      // non-zero = "identical planes" until a mismatch clears it
+    if (e != cudaSuccess) return (int)e;
+    const int64_t total = B * plane;
+    const unsigned blocks = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 16);
+    planes_equal_kernel<<<blocks, 256, 0, s>>>(in, (int)C, plane, total, flag);
+    count_launch();
+    return finish_launch();
 }
 
 }  // namespace sstem

@@ -43,7 +43,7 @@ int launch_tail_bwd_variant(const float* g, const float* frame, int64_t frame_bs
     auto kern = sepconv_bwd_taps_k51_kernel<1, G, R, VEC, false, WV, WH, false, true>;
     if (int e = set_smem_once(kern, smem, done)) return e;
     dim3 grid((unsigned)((W + Geo<G, R>::TILE_W - 1) / Geo<G, R>::TILE_W), (unsigned)((H + R - 1) / R), (unsigned)B);
-    kern<<<grid, 128, smem_used, s>>>(g, frame, v, h, gv, gh, 1, 0, H, W, 1, frame_bstride, cs, nplanes, gscale);
+    kern<<<grid, 128, smem_used, s>>>(g, frame, v, h, gv, gh, 1, 0, H, W, 1, frame_bstride, cs, nplanes, gscale, nullptr, 0);
     count_launch();
     return finish_launch();
 }

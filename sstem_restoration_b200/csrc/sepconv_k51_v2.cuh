@@ -36,7 +36,9 @@ constexpr size_t V2_BWD_SMEM = V2_WIN_BYTES + V2_VT_BYTES + 128;
 // NCHW planes c0..c0+2 of `in` [B,C,IH,IW] -> out [B,IH,IW] float4 (x, y, z = the three channels, w = 0)
 template <bool VEC4>
 __global__ void __launch_bounds__(256)
-repack_nchw3_to_nhwc4_kernel(const float* __restrict__ in, float4* __restrict__ out, int C, int c0, int64_t plane, int64_t total) {
+repack_nchw3_to_nhwc4_kernel(const float* __restrict__ in, float4* __restrict__ out, int C, int c0, int64_t plane, int64_t total,
+                             const int* gate, int gate_want) {
+    SSTEM_GATE_RETURN(gate, gate_want);
     const int64_t step = (int64_t)gridDim.x * blockDim.x;
     if (VEC4) {                                           // plane % 4 == 0 and 16-byte aligned base: 4 pixels per thread
         const int64_t n4 = total >> 2, p4 = plane >> 2;
@@ -62,7 +64,9 @@ repack_nchw3_to_nhwc4_kernel(const float* __restrict__ in, float4* __restrict__ 
 // One plane (channel c0) of in [B,C,IH,IW] -> out [B,IH,IWP] with the row pitch IWP rounded up to 4 floats, so that
 // the copy can be the source of a tensor map (16-byte strides); the pad columns are zero.
 __global__ void __launch_bounds__(256)
-repack_plane_pitch_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int c0, int IH, int IW, int IWP, int64_t total) {
+repack_plane_pitch_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int c0, int IH, int IW, int IWP, int64_t total,
+                          const int* gate, int gate_want) {
+    SSTEM_GATE_RETURN(gate, gate_want);
     const int64_t step = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
         const int x = (int)(i % IWP);
@@ -71,6 +75,21 @@ repack_plane_pitch_kernel(const float* __restrict__ in, float* __restrict__ out,
         const int64_t b = r / IH;
         out[i] = x < IW ? __ldg(in + ((b * C + c0) * IH + y) * (int64_t)IW + x) : 0.f;
     }
+}
+
+// flag = 1 iff every channel plane of in [B,C,plane] is bit-identical to plane 0 of its image (gray sections replicated
+// x3: sff_scripts_interp/data/data_provider.py:136-137).  *flag must be 1 on entry; any mismatch clears it.
+__global__ void __launch_bounds__(256)
+planes_equal_kernel(const float* __restrict__ in, int C, int64_t plane, int64_t total /* B * plane */, int* __restrict__ flag) {
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    bool same = true;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total && same; i += step) {
+        const int64_t b = i / plane, p = i - b * plane;
+        const unsigned* s = reinterpret_cast<const unsigned*>(in) + b * C * plane + p;
+        const unsigned ref = __ldg(s);
+        for (int c = 1; c < C; ++c) same = same && (__ldg(s + c * plane) == ref);
+    }
+    if (!__all_sync(0xffffffffu, same) && (threadIdx.x & 31) == 0) *flag = 0;
 }
 
 // NCHW taps [B,51,H,W] -> tile-major [B][ceil(H/8)][ceil(W/8)][51][8][8] (zero outside the image): the layout the

@@ -179,7 +179,8 @@ __global__ void __launch_bounds__(V3_WARPS * 32, 2)
 sepconv_bwd_taps_k51_v3_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_v,
                                const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_g,
                                float* __restrict__ gv, float* __restrict__ gh, int* __restrict__ next_tile_counter,
-                               const V3Shape sh) {
+                               const V3Shape sh, const int* gate, int gate_want) {
+    SSTEM_GATE_RETURN(gate, gate_want);
     constexpr int G = 4, R = 4, NP = 2, NT = 13;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // the shuffle tells the compiler that `warp` -- and with it every ring / barrier address and TMA coordinate below --
@@ -454,7 +455,8 @@ template <int CC, bool TILED>
 __global__ void __launch_bounds__(V3_WARPS * 32, 2)
 sepconv_fwd_k51_v3_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_v,
                           const __grid_constant__ CUtensorMap map_h, const F3Tiled tl, float* __restrict__ out,
-                          int* __restrict__ next_tile_counter, const V3Shape sh, int replicas) {
+                          int* __restrict__ next_tile_counter, const V3Shape sh, int replicas, const int* gate, int gate_want) {
+    SSTEM_GATE_RETURN(gate, gate_want);
     constexpr int G = 4, R = F3_R, NP = 4, NT = 13;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;

@@ -34,29 +34,44 @@ def set_strict_order(enabled: bool) -> None:
     _STRICT = bool(enabled)
 
 
-_GRAY = os.environ.get("SSTEM_SEPCONV_GRAY", "off")        # off | assert | detect
+_GRAY = os.environ.get("SSTEM_SEPCONV_GRAY", "auto")       # off | assert | detect | auto
+_AUTO_MIN_PIXELS = 1 << 19                                  # auto: detect from B*H*W of this size on (detection costs ~15 us + two empty launches)
 
 
 def set_gray_replicated(mode) -> None:
-    """Opt-in shortcut for the reference's actual inputs: grayscale sections replicated x3
+    """Shortcut for the reference's actual inputs: grayscale sections replicated x3
     (sff_scripts_interp/data/data_provider.py:136-137), i.e. identical channel planes.
 
-    ``"assert"``: the caller guarantees it; ``"detect"``: every forward compares the planes
-    (one small reduction + a host sync) and uses the shortcut only when they are equal;
-    ``"off"`` (default): always the general path.  Forward results are bit-identical either
-    way; tap gradients agree to fp32 rounding."""
+    ``"assert"``: the caller guarantees it.  ``"detect"``: every forward compares the planes ON THE DEVICE (one streaming
+    kernel writing a device flag) and launches both the one-plane and the general path gated on that flag -- no host
+    synchronisation; the backward reads the same flag.  ``"auto"`` (default): ``"detect"`` for calls of at least 2^19
+    output pixels (where the detection's ~20 us are below 3 %), the general path below.  ``"off"``: always the general
+    path.  Forward results are bit-identical either way; tap gradients agree to fp32 rounding."""
     global _GRAY
     mode = {True: "assert", False: "off", None: "off"}.get(mode, mode)
-    if mode not in ("off", "assert", "detect"):
-        raise ValueError("mode must be 'off', 'assert' or 'detect'")
+    if mode not in ("off", "assert", "detect", "auto"):
+        raise ValueError("mode must be 'off', 'assert', 'detect' or 'auto'")
     _GRAY = mode
 
 
+def _gray_mode(input, K) -> str:
+    """-> 'off' | 'assert' | 'detect' for this call."""
+    if _GRAY == "off" or _STRICT or input.size(1) < 2 or K != 51:
+        return "off"
+    if _GRAY == "auto":
+        B, _, ih, iw = input.shape
+        return "detect" if B * (ih - 50) * (iw - 50) >= _AUTO_MIN_PIXELS else "off"
+    return _GRAY
+
+
 def _is_gray(input) -> bool:
+    """Host-side decision (used by the fused tail and the tiled forward): assert -> True; detect/auto -> compare (syncs)."""
     if _GRAY == "off" or _STRICT or input.size(1) < 2:
         return False
     if _GRAY == "assert":
         return True
+    if _GRAY == "auto":
+        return False
     return all(bool(torch.equal(input[:, 0], input[:, c])) for c in range(1, input.size(1)))
 
 
@@ -114,10 +129,20 @@ def _forward_impl(ctx, input, vertical, horizontal, filter_size):
     B, C = input.size(0), input.size(1)
     output = torch.empty((B, C, oh, ow), dtype=input.dtype, device=input.device)
     ctx.gray = False
+    ctx.gray_flag = None
     if output.numel() == 0:
         return output
-    ctx.gray = K == 51 and _is_gray(input)
+    mode = _gray_mode(input, K)
     # the library launches on the device that owns `output`; only the stream has to be the caller's
+    if mode == "detect":
+        ctx.gray_flag = torch.empty(1, dtype=torch.int32, device=input.device)      # written and consumed on the device
+        code = _lib.load().sstem_sepconv_forward_detect(
+            input.data_ptr(), vertical.data_ptr(), horizontal.data_ptr(), output.data_ptr(),
+            B, C, oh, ow, K, _flags(False), ctx.gray_flag.data_ptr(), _stream_ptr(input))
+        if code:
+            _lib.check(code, "sstem_sepconv_forward_detect")
+        return output
+    ctx.gray = mode == "assert"
     code = _lib.load().sstem_sepconv_forward(
         input.data_ptr(), vertical.data_ptr(), horizontal.data_ptr(), output.data_ptr(),
         B, C, oh, ow, K, _flags(ctx.gray), _stream_ptr(input))
@@ -138,12 +163,15 @@ def _backward_impl(ctx, grad_output):
     grad_vertical = torch.empty_like(vertical) if need_v else None
     grad_horizontal = torch.empty_like(horizontal) if need_h else None
     if (need_in or need_v or need_h) and grad_output.numel() > 0:
-        code = _lib.load().sstem_sepconv_backward(
-            grad_output.data_ptr(), input.data_ptr(), vertical.data_ptr(), horizontal.data_ptr(),
-            grad_input.data_ptr() if need_in else None,
-            grad_vertical.data_ptr() if need_v else None,
-            grad_horizontal.data_ptr() if need_h else None,
-            B, C, oh, ow, K, _flags(getattr(ctx, "gray", False)), _stream_ptr(input))
+        flag = getattr(ctx, "gray_flag", None)
+        ptrs = (grad_output.data_ptr(), input.data_ptr(), vertical.data_ptr(), horizontal.data_ptr(),
+                grad_input.data_ptr() if need_in else None,
+                grad_vertical.data_ptr() if need_v else None,
+                grad_horizontal.data_ptr() if need_h else None)
+        if flag is not None:
+            code = _lib.load().sstem_sepconv_backward_detect(*ptrs, B, C, oh, ow, K, _flags(False), flag.data_ptr(), _stream_ptr(input))
+        else:
+            code = _lib.load().sstem_sepconv_backward(*ptrs, B, C, oh, ow, K, _flags(getattr(ctx, "gray", False)), _stream_ptr(input))
         if code:
             _lib.check(code, "sstem_sepconv_backward")
     return grad_input, grad_vertical, grad_horizontal
@@ -220,8 +248,10 @@ class _InterpolationTail(torch.autograd.Function):
         if bs1 != bs2:
             i1, i2 = i1.contiguous(), i2.contiguous()
             bs1 = bs2 = C * H * W
-        gray = C > 1 and _GRAY != "off" and (
-            _GRAY == "assert" or all(bool(torch.equal(f[:, 0], f[:, c])) for f in (i1, i2) for c in range(1, C)))
+        # "detect" compares on the host here (the tail's general-channel mode already folds the channel mean into the window
+        # load, so the shortcut is worth 20 %, not 2x); "auto" does not pay a synchronisation for that
+        gray = C > 1 and (_GRAY == "assert" or (
+            _GRAY == "detect" and all(bool(torch.equal(f[:, 0], f[:, c])) for f in (i1, i2) for c in range(1, C))))
         out = torch.empty((B, 1, H, W), dtype=torch.float32, device=i1.device)
         ctx.save_for_backward(i1, i2, k1v, k1h, k2v, k2h)
         ctx.tail = (bs1, gray)

@@ -321,6 +321,45 @@ def test_gray_replicated_shortcut():
     assert torch.equal(out2, pkg.SeparableConvolution.apply(t2, tv, th))
 
 
+def test_gray_detection_on_the_device_at_training_size():
+    """"detect" / "auto": the planes are compared by a kernel, both paths are launched gated on a DEVICE flag (no host sync).
+    The flag must say gray exactly when the planes are identical, the forward must be bit-identical to the general path both
+    ways, and the tap gradients must agree with the general path's to fp32 rounding."""
+    from sstem_restoration_b200 import _lib
+    pkg = _ops()
+    dev = "cuda"
+    B, H, W = 2, 512, 512
+    gen = torch.Generator(device=dev).manual_seed(21)
+    plane = torch.rand((B, 1, H + 50, W + 50), device=dev, generator=gen)
+    gray = plane.expand(B, 3, H + 50, W + 50).contiguous()
+    color = gray.clone()
+    color[1, 2, 300, 17] += 0.25                                  # one differing element in the last image
+    v = torch.softmax(torch.randn((B, 51, H, W), device=dev, generator=gen), 1)
+    h = torch.softmax(torch.randn((B, 51, H, W), device=dev, generator=gen), 1)
+    g = torch.randn((B, 3, H, W), device=dev, generator=gen)
+    lib = _lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    for inp, want in ((gray, True), (color, False)):
+        pkg.set_gray_replicated("off")
+        ref_out, _, ref_gv, ref_gh = _bwd(inp, v, h, g, need_input=False)
+        flag = torch.full((1,), 77, dtype=torch.int32, device=dev)
+        out = torch.empty_like(ref_out)
+        assert lib.sstem_sepconv_forward_detect(inp.data_ptr(), v.data_ptr(), h.data_ptr(), out.data_ptr(), B, 3, H, W, 51, 0,
+                                                flag.data_ptr(), st) == 0
+        assert (int(flag.item()) != 0) == want and torch.equal(out, ref_out)
+        for mode in ("detect", "auto"):
+            pkg.set_gray_replicated(mode)
+            try:
+                out2, _, gv, gh = _bwd(inp, v, h, g, need_input=False)
+            finally:
+                pkg.set_gray_replicated("off")
+            assert torch.equal(out2, ref_out), mode
+            tol = 2e-5 * max(1.0, float(ref_gv.abs().max()), float(ref_gh.abs().max()))
+            assert float((gv - ref_gv).abs().max()) <= tol and float((gh - ref_gh).abs().max()) <= tol, mode
+            if not want:                                          # planes differ: the general path ran, bit for bit
+                assert torch.equal(gv, ref_gv) and torch.equal(gh, ref_gh)
+
+
 def test_window_rows_outside_a_pixels_support_cannot_leak_nan():
     """The tuned kernels walk 58 input rows per 8-row tile; a row below a pixel's own 51-row window
     is multiplied by a zero weight internally.  A NaN / Inf there must not reach that pixel."""
