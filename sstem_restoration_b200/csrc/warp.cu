@@ -218,6 +218,7 @@ __device__ __noinline__ void warp_partial_tile(const float* s_fx, const float* s
         const int n_in = max(s_box[6], 1);
         // window origin: mean tap position minus half the window (x rounded down to 4 floats = 16 bytes)
         const int wx0 = (j00 + s_box[4] / n_in - WT_BW / 2 + 1) & ~3, wy0 = i0 + s_box[5] / n_in - WT_BH / 2 + 1;
+        constexpr bool use_window = true;                  // (the caller sends tiles with a huge bounding box elsewhere)
         if (tid == 0) {
             mbar_expect_tx(bar1, (unsigned)(CT * WT_BH * WT_BW * sizeof(float)));
             tma_load_3d(s_im, map_im, bar1, wx0, wy0, b * CT);
@@ -227,11 +228,11 @@ __device__ __noinline__ void warp_partial_tile(const float* s_fx, const float* s
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int rx = xa[q] - wx0, ry = ya[q] - wy0;
-            in_win[q] = rx >= 0 && rx + dxs[q] < WT_BW && ry >= 0 && ry + dys[q] < WT_BH;
+            in_win[q] = use_window && rx >= 0 && rx + dxs[q] < WT_BW && ry >= 0 && ry + dys[q] < WT_BH;
             o00[q] = ry * WT_BW + rx;
         }
         mbar_wait(bar1, 0);
-#pragma unroll 1
+#pragma unroll                                              // all channels' global gathers of a pixel in flight together
         for (int c = 0; c < CT; ++c) {
             const float* im = moving + ((int64_t)b * CT + c) * plane;
             const float* sc = s_im + c * (WT_BH * WT_BW);
@@ -260,6 +261,9 @@ __device__ __noinline__ void warp_partial_tile(const float* s_fx, const float* s
         }
 }
 
+#ifndef SSTEM_WARP_PARTIAL
+#define SSTEM_WARP_PARTIAL 1
+#endif
 #ifndef SSTEM_WARP_TMA_MINB
 #define SSTEM_WARP_TMA_MINB 7
 #endif
@@ -393,7 +397,34 @@ warp_torch_tma_kernel(const __grid_constant__ CUtensorMap map_fx, const __grid_c
         // nothing would send every pixel of the tile to global-memory gathers (measured 1.1 TB/s on an N(0, 5 px) flow);
         // instead the largest window is centred on the tile's mean tap position, fetched with the same single TMA box,
         // and each PIXEL decides: all four taps inside the window -> shared memory, else -> its own global gathers.
-        warp_partial_tile<CT>(s_fx, s_fy, s_im, s_box, &bar[1], &map_im, moving, obase, b, i0, j00, H, W);
+        // A fold line through the tile splits its taps into two clusters tens of pixels apart: no window serves both, and
+        // these few tiles (1.7 % on the SFF fold flow) set the kernel's tail -- they take the plain global gathers below.
+        // Only a bounding box that outruns the window moderately (a rough but zero-mean flow: N(0, 5 px) gives ~38 x 98) goes to
+        // the out-of-line path; tiles next to a fold line (100-200 columns wide) were measured faster on the plain gathers.
+        const bool moderate = SSTEM_WARP_PARTIAL && (bx1 - bx0 < WT_BW + 32) && (by1 - by0 < 2 * WT_BH);
+        if (moderate) {
+            warp_partial_tile<CT>(s_fx, s_fy, s_im, s_box, &bar[1], &map_im, moving, obase, b, i0, j00, H, W);
+            return;
+        }
+#pragma unroll 1
+        for (int c = 0; c < CT; ++c) {
+            const float* im = moving + ((int64_t)b * CT + c) * plane;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int x0 = xa[q], y0 = ya[q], x1 = x0 + dxs[q], y1 = y0 + dys[q];
+                const bool vx0 = (unsigned)x0 < (unsigned)W, vx1 = (unsigned)x1 < (unsigned)W;
+                const bool vy0 = (unsigned)y0 < (unsigned)H, vy1 = (unsigned)y1 < (unsigned)H;
+                const float Ia = (vy0 && vx0) ? __ldg(im + (int64_t)y0 * W + x0) : 0.f;
+                const float Ib = (vy1 && vx0) ? __ldg(im + (int64_t)y1 * W + x0) : 0.f;
+                const float Ic = (vy0 && vx1) ? __ldg(im + (int64_t)y0 * W + x1) : 0.f;
+                const float Id = (vy1 && vx1) ? __ldg(im + (int64_t)y1 * W + x1) : 0.f;
+                float r = __fadd_rn(__fmul_rn(wa[q], Ia), __fmul_rn(wb[q], Ib));
+                r = __fadd_rn(r, __fmul_rn(wc[q], Ic));
+                r = __fadd_rn(r, __fmul_rn(wd[q], Id));
+                const int i = i0 + warp + WT_HALF * (q >> 1), j = j00 + lane + 32 * (q & 1);
+                if (i < H && j < W) __stcs(obase + c * plane + (int64_t)i * W + j, r);
+            }
+        }
     }
 }
 
