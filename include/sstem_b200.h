@@ -253,6 +253,15 @@ int sstem_prediction_to_u8(const float* pred, uint8_t* section, int64_t batch, i
 int sstem_warp_stitch_u8(const float* warped, const uint8_t* interp, uint8_t* gray_out, uint8_t* stitch_out,
                          int64_t B, int64_t C, int64_t H, int64_t W, void* stream);
 
+/* The two steps above in ONE kernel: SpatialTransformation(moving, flow) with the stitch assembly as its epilogue (the float32
+ * warped image is neither written nor read back).  moving [B,C,H,W] float32 (C = 1 or 3), flow as sstem_warp_forward,
+ * interp / gray_out (nullable) / stitch_out uint8 [B,H,W].  Bit-equal to sstem_warp_forward + sstem_warp_stitch_u8.
+ * Shapes the TMA kernel does not take (W % 4 != 0, interleaved flow, H*W % 4 != 0 excluded) run the two steps through a
+ * stream-ordered scratch image. */
+int sstem_warp_stitch_forward(const float* moving, const float* flow, const int64_t flow_strides[4],
+                              const uint8_t* interp, uint8_t* gray_out, uint8_t* stitch_out,
+                              int64_t B, int64_t C, int64_t H, int64_t W, void* stream);
+
 /*
  * Tile-major taps (the layout a tap PRODUCER should emit -- the last Conv2d(51,51,3x3) of
  * IFNet._kernel_module, sff_scripts_interp/model/model_interp.py:129-137, writes [B,51,H,W] today and sepconv re-reads it

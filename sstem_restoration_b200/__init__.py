@@ -20,12 +20,12 @@ from .sepconv import (  # noqa: F401
 from .warp import SpatialTransformation, image_warp  # noqa: F401
 from .host import sepconv_forward_backward_host, join_host_pipeline  # noqa: F401
 from .stack_io import sections_to_input, prediction_to_uint8  # noqa: F401
-from .stack import restore_stack, warp_stitch  # noqa: F401
+from .stack import restore_stack, warp_stitch, warp_and_stitch  # noqa: F401
 from . import shard, synth, sff_sim  # noqa: F401
 
 __all__ = [
     "SeparableConvolution", "FunctionSepconv", "ModuleSepconv", "set_strict_order", "set_gray_replicated",
     "interpolation_tail", "ModuleInterpolationTail", "taps_to_tiled", "sepconv_forward_tiled",
     "SpatialTransformation", "image_warp", "sepconv_forward_backward_host", "join_host_pipeline", "SstemError", "launch_count", "fp32_peak_probe",
-    "sections_to_input", "prediction_to_uint8", "restore_stack", "warp_stitch", "shard", "synth", "sff_sim",
+    "sections_to_input", "prediction_to_uint8", "restore_stack", "warp_stitch", "warp_and_stitch", "shard", "synth", "sff_sim",
 ]

@@ -37,7 +37,7 @@ WARP_NEAREST = 1
 EXPORTED_SYMBOLS = (
     "sstem_sepconv_forward", "sstem_sepconv_backward", "sstem_interp_tail_forward", "sstem_interp_tail_backward",
     "sstem_warp_forward", "sstem_image_warp", "sstem_sff_degrade", "sstem_sff_contrast",
-    "sstem_sections_to_input", "sstem_prediction_to_u8", "sstem_warp_stitch_u8",
+    "sstem_sections_to_input", "sstem_prediction_to_u8", "sstem_warp_stitch_u8", "sstem_warp_stitch_forward",
     "sstem_taps_tiled_elems", "sstem_taps_to_tiled", "sstem_sepconv_forward_tiled",
     "sstem_sepconv_forward_detect", "sstem_sepconv_backward_detect",
     "sstem_fp32_peak_probe", "sstem_launch_count", "sstem_abi_version", "sstem_error_string",
@@ -86,6 +86,8 @@ def load() -> ctypes.CDLL:
         lib.sstem_prediction_to_u8.restype = ctypes.c_int
         lib.sstem_warp_stitch_u8.argtypes = [_c_p] * 4 + [_c_i64] * 4 + [_c_p]
         lib.sstem_warp_stitch_u8.restype = ctypes.c_int
+        lib.sstem_warp_stitch_forward.argtypes = [_c_p, _c_p, ctypes.POINTER(_c_i64), _c_p, _c_p, _c_p, _c_i64, _c_i64, _c_i64, _c_i64, _c_p]
+        lib.sstem_warp_stitch_forward.restype = ctypes.c_int
         lib.sstem_taps_tiled_elems.argtypes = [_c_i64] * 3
         lib.sstem_taps_tiled_elems.restype = _c_i64
         lib.sstem_taps_to_tiled.argtypes = [_c_p, _c_p, _c_i64, _c_i64, _c_i64, _c_p]

@@ -267,12 +267,25 @@ __device__ __noinline__ void warp_partial_tile(const float* s_fx, const float* s
 #ifndef SSTEM_WARP_TMA_MINB
 #define SSTEM_WARP_TMA_MINB 7
 #endif
+// STITCH: the output assembly of the correction module as the kernel's epilogue -- sff_scripts_fusion/inference.py:163-171:
+// (warped * 255).astype(uint8) -> PIL 'L' -> stitch with the interpolated section where the warped one is < 2 -- so the
+// float32 warped image is never written (12 B/pixel at C = 3) nor read back by a separate kernel; only uint8 leaves.
+struct WarpStitch {
+    const uint8_t* interp;                              // [B,H,W] uint8, the interpolated section
+    uint8_t* gray;                                      // [B,H,W] uint8 out (nullable): the warped section, 'L'
+    uint8_t* stitch;                                    // [B,H,W] uint8 out
+};
 template <int CT>
+__device__ __forceinline__ unsigned luma_term(int c, float r) {
+    const unsigned u = (unsigned)(uint8_t)(int)__fmul_rn(r, 255.0f);        // astype(np.uint8)
+    return CT == 3 ? (c == 0 ? 19595u : (c == 1 ? 38470u : 7471u)) * u : u; // PIL RGB -> L, fixed point
+}
+template <int CT, bool STITCH = false>
 __global__ void __launch_bounds__(WT_THREADS, SSTEM_WARP_TMA_MINB)
 warp_torch_tma_kernel(const __grid_constant__ CUtensorMap map_fx, const __grid_constant__ CUtensorMap map_fy,
                       const __grid_constant__ CUtensorMap map_im, const __grid_constant__ CUtensorMap map_im_small,
                       const __grid_constant__ CUtensorMap map_im_mid, const float* __restrict__ moving,
-                      float* __restrict__ out, int H, int W) {
+                      float* __restrict__ out, int H, int W, const WarpStitch st) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* s_im = reinterpret_cast<float*>(smem_raw);                       // [CT][BH][BW]
     float* s_fx = s_im + CT * WT_BH * WT_BW;                                // [TH][TW]
@@ -341,6 +354,19 @@ warp_torch_tma_kernel(const __grid_constant__ CUtensorMap map_fx, const __grid_c
     for (int q = 0; q < 4; ++q) offa[q] = (ya[q] - by0) * pitch + (xa[q] - bx0);
     const int64_t plane = (int64_t)H * W;
     float* obase = out + (int64_t)b * CT * plane;
+    [[maybe_unused]] unsigned lum[4] = {0u, 0u, 0u, 0u};  // STITCH: fixed-point luma of the thread's 4 pixels
+    [[maybe_unused]] auto stitch_store = [&]() {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int i = i0 + warp + WT_HALF * (q >> 1), j = j00 + lane + 32 * (q & 1);
+            if (i < H && j < W) {
+                const unsigned L = CT == 3 ? (lum[q] + 0x8000u) >> 16 : lum[q];
+                const int64_t idx = (int64_t)b * plane + (int64_t)i * W + j;
+                if (st.gray) st.gray[idx] = (uint8_t)L;
+                st.stitch[idx] = L >= 2u ? (uint8_t)L : st.interp[idx];
+            }
+        }
+    };
     if (fits) {
         // word offsets of the four taps of each pixel inside one channel plane of the window, and the
         // pixel's offset inside one output plane: computed once, shared by all channels
@@ -384,14 +410,18 @@ warp_torch_tma_kernel(const __grid_constant__ CUtensorMap map_fx, const __grid_c
                     const float2 pc = __fmul2_rn(wc2[h], Ic), pd = __fmul2_rn(wd2[h], Id);
                     const float rx = __fadd_rn(__fadd_rn(__fadd_rn(pa.x, pb.x), pc.x), pd.x);
                     const float ry = __fadd_rn(__fadd_rn(__fadd_rn(pa.y, pb.y), pc.y), pd.y);
-                    if (ok[q0]) __stcs(oc + ooff[q0], rx);
-                    if (ok[q1]) __stcs(oc + ooff[q1], ry);
+                    if constexpr (STITCH) { lum[q0] += luma_term<CT>(c, rx); lum[q1] += luma_term<CT>(c, ry); }
+                    else {
+                        if (ok[q0]) __stcs(oc + ooff[q0], rx);
+                        if (ok[q1]) __stcs(oc + ooff[q1], ry);
+                    }
                 }
             }
         };
         if (small) blend(std::integral_constant<int, WT_SH * WT_SW>{});
         else if (mid) blend(std::integral_constant<int, WT_MH * WT_MW>{});
         else blend(std::integral_constant<int, WT_BH * WT_BW>{});
+        if constexpr (STITCH) stitch_store();
     } else {
         // The taps of this tile spread beyond the largest window (a fold line crosses it, or the flow is rough).  All-or-
         // nothing would send every pixel of the tile to global-memory gathers (measured 1.1 TB/s on an N(0, 5 px) flow);
@@ -401,7 +431,7 @@ warp_torch_tma_kernel(const __grid_constant__ CUtensorMap map_fx, const __grid_c
         // these few tiles (1.7 % on the SFF fold flow) set the kernel's tail -- they take the plain global gathers below.
         // Only a bounding box that outruns the window moderately (a rough but zero-mean flow: N(0, 5 px) gives ~38 x 98) goes to
         // the out-of-line path; tiles next to a fold line (100-200 columns wide) were measured faster on the plain gathers.
-        const bool moderate = SSTEM_WARP_PARTIAL && (bx1 - bx0 < WT_BW + 32) && (by1 - by0 < 2 * WT_BH);
+        const bool moderate = SSTEM_WARP_PARTIAL && !STITCH && (bx1 - bx0 < WT_BW + 32) && (by1 - by0 < 2 * WT_BH);
         if (moderate) {
             warp_partial_tile<CT>(s_fx, s_fy, s_im, s_box, &bar[1], &map_im, moving, obase, b, i0, j00, H, W);
             return;
@@ -422,9 +452,11 @@ warp_torch_tma_kernel(const __grid_constant__ CUtensorMap map_fx, const __grid_c
                 r = __fadd_rn(r, __fmul_rn(wc[q], Ic));
                 r = __fadd_rn(r, __fmul_rn(wd[q], Id));
                 const int i = i0 + warp + WT_HALF * (q >> 1), j = j00 + lane + 32 * (q & 1);
-                if (i < H && j < W) __stcs(obase + c * plane + (int64_t)i * W + j, r);
+                if constexpr (STITCH) lum[q] += luma_term<CT>(c, r);
+                else if (i < H && j < W) __stcs(obase + c * plane + (int64_t)i * W + j, r);
             }
         }
+        if constexpr (STITCH) stitch_store();
     }
 }
 
@@ -443,10 +475,10 @@ static bool make_map3(CUtensorMap* m, const float* base, int64_t W, int64_t H, i
 }
 
 // returns 0 on launch, >0 cuda error, -1000 when the TMA path does not apply (caller falls back)
-template <int CT>
+template <int CT, bool STITCH = false>
 static int try_launch_warp_tma(const float* moving, const float* flow, const int64_t* fs, float* out,
-                               int64_t B, int64_t H, int64_t W, cudaStream_t s) {
-    if ((W & 3) || fs[2] != 1 || !aligned16(moving) || !aligned16(flow) || !aligned16(out)) return -1000;
+                               int64_t B, int64_t H, int64_t W, cudaStream_t s, WarpStitch st = WarpStitch{nullptr, nullptr, nullptr}) {
+    if ((W & 3) || fs[2] != 1 || !aligned16(moving) || !aligned16(flow) || (!STITCH && !aligned16(out))) return -1000;
     if ((fs[0] & 3) || (fs[1] & 3) || (fs[3] & 3) || fs[1] < W || B > 65535 || (H + WT_TH - 1) / WT_TH > 65535) return -1000;
     CUtensorMap mfx, mfy, mim, mims, mimm;
     if (!make_map3(&mfx, flow, W, H, B, fs[1], fs[0], WT_TW, WT_TH, 1)) return -1000;
@@ -459,12 +491,12 @@ static int try_launch_warp_tma(const float* moving, const float* flow, const int
     int dev = 0;
     cudaGetDevice(&dev);
     if (!done.test(dev)) {
-        cudaError_t e = cudaFuncSetAttribute(warp_torch_tma_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(warp_torch_tma_kernel<CT, STITCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         done.set(dev);
     }
     dim3 grid((unsigned)((W + WT_TW - 1) / WT_TW), (unsigned)((H + WT_TH - 1) / WT_TH), (unsigned)B);
-    warp_torch_tma_kernel<CT><<<grid, WT_THREADS, smem, s>>>(mfx, mfy, mim, mims, mimm, moving, out, (int)H, (int)W);
+    warp_torch_tma_kernel<CT, STITCH><<<grid, WT_THREADS, smem, s>>>(mfx, mfy, mim, mims, mimm, moving, out, (int)H, (int)W, st);
     count_launch();
     return finish_launch();
 }
@@ -607,6 +639,32 @@ extern "C" int sstem_warp_forward(const float* moving, const float* flow, const 
 #undef SSTEM_WARP_LAUNCH
     count_launch();
     return finish_launch();
+}
+
+extern "C" int sstem_warp_stitch_u8(const float* warped, const uint8_t* interp, uint8_t* gray_out, uint8_t* stitch_out,
+                                    int64_t B, int64_t C, int64_t H, int64_t W, void* stream);
+
+extern "C" int sstem_warp_stitch_forward(const float* moving, const float* flow, const int64_t flow_strides[4],
+                                         const uint8_t* interp, uint8_t* gray_out, uint8_t* stitch_out,
+                                         int64_t B, int64_t C, int64_t H, int64_t W, void* stream) {
+    if (!moving || !flow || !flow_strides || !interp || !stitch_out) return SSTEM_E_NULL;
+    if (B <= 0 || H <= 0 || W <= 0 || (C != 1 && C != 3) || H > (1 << 24) || W > (1 << 24)) return SSTEM_E_SHAPE;
+    if (!aligned4(moving) || !aligned4(flow)) return SSTEM_E_ALIGN;
+    DeviceGuard guard(stitch_out);
+    if (guard.err) return guard.err;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (H * W > INT32_MAX) return SSTEM_E_SHAPE;
+    const WarpStitch st{interp, gray_out, stitch_out};
+    const int r = (C == 3) ? try_launch_warp_tma<3, true>(moving, flow, flow_strides, nullptr, B, H, W, s, st)
+                           : try_launch_warp_tma<1, true>(moving, flow, flow_strides, nullptr, B, H, W, s, st);
+    if (r != -1000) return r;
+    // shapes the TMA kernel does not take: the two steps one after the other through a stream-ordered scratch image
+    float* tmp = nullptr;
+    if (workspace_alloc(reinterpret_cast<void**>(&tmp), (size_t)(B * C * H * W) * sizeof(float), s)) return (int)cudaErrorMemoryAllocation;
+    int e = sstem_warp_forward(moving, flow, flow_strides, tmp, B, C, H, W, SSTEM_LAYOUT_NCHW, stream);
+    if (!e) e = sstem_warp_stitch_u8(tmp, interp, gray_out, stitch_out, B, C, H, W, stream);
+    cudaFreeAsync(tmp, s);
+    return e;
 }
 
 extern "C" int sstem_image_warp(const void* im, int32_t pix_type, const float* flow,

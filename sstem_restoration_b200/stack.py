@@ -59,6 +59,36 @@ def warp_stitch(warped: torch.Tensor, interp_u8: torch.Tensor, want_gray: bool =
     return gray, stitch
 
 
+def warp_and_stitch(moving: torch.Tensor, flow: torch.Tensor, interp_u8: torch.Tensor, want_gray: bool = True, out=None):
+    """``SpatialTransformation(moving, flow)`` followed by :func:`warp_stitch`, as ONE kernel: the stitch assembly is the warp
+    kernel's epilogue, so the float32 warped image is never written or read back (sff_scripts_fusion/inference.py:150 +
+    :163-171).  ``moving`` [B,C,H,W] float32 CUDA (C = 1 or 3), ``flow`` [B,H,W,2] (any strides), ``interp_u8`` [B,H,W].
+    Returns ``(warped_gray_u8, stitch_u8)``; bit-equal to the two separate calls."""
+    if not (moving.is_cuda and flow.is_cuda and interp_u8.is_cuda):
+        raise _lib.SstemError("warp_and_stitch: CUDA tensors required; there is no CPU fallback")
+    if moving.dtype != torch.float32 or flow.dtype != torch.float32 or interp_u8.dtype != torch.uint8:
+        raise TypeError("warp_and_stitch: float32 image / flow and uint8 interpolated section required")
+    B, C, H, W = moving.shape
+    if tuple(flow.shape) != (B, H, W, 2) or tuple(interp_u8.shape) != (B, H, W):
+        raise ValueError("warp_and_stitch: flow must be [B,H,W,2] and interp_u8 [B,H,W] matching moving [B,C,H,W]")
+    moving, interp_u8 = moving.contiguous(), interp_u8.contiguous()
+    if out is not None:
+        gray, stitch = out
+        want_gray = gray is not None
+    else:
+        gray = torch.empty((B, H, W), dtype=torch.uint8, device=moving.device) if want_gray else None
+        stitch = torch.empty((B, H, W), dtype=torch.uint8, device=moving.device)
+    if stitch.numel():
+        import ctypes
+        strides = (ctypes.c_int64 * 4)(*flow.stride())
+        code = _lib.load().sstem_warp_stitch_forward(moving.data_ptr(), flow.data_ptr(), strides, interp_u8.data_ptr(),
+                                                     gray.data_ptr() if want_gray else None, stitch.data_ptr(), B, C, H, W,
+                                                     torch.cuda.current_stream(moving.device).cuda_stream)
+        if code:
+            _lib.check(code, "sstem_warp_stitch_forward")
+    return gray, stitch
+
+
 class _SectionCache:
     """uint8 sections of this rank on the device: each is uploaded once, on a copy stream, ahead of its first use."""
 
@@ -105,8 +135,7 @@ def restore_stack(stack: torch.Tensor, taps_fn: Callable, flow_fn: Optional[Call
         interp = prediction_to_uint8(interpolation_tail(x[:, :3], x[:, 3:6], k1v, k1h, k2v, k2h))
         if flow_fn:                                                  # the correction module's flow net (out of scope)
             xk = sections_to_input(stack[k])                         # [1,3,H,W]: input_sff
-            warped = SpatialTransformation()(xk[:, :1], flow_fn(k, xk, interp))   # flow [1,H,W,2], any strides; planes identical
-            warped_gray, stitch = warp_stitch(warped, interp)
+            warped_gray, stitch = warp_and_stitch(xk[:, :1], flow_fn(k, xk, interp), interp)   # one kernel; planes identical
 
     Returns a dict of uint8 tensors -- ``interp`` and, with ``flow_fn``, ``warped`` and ``stitch`` -- plus ``stats``.
 
@@ -154,8 +183,8 @@ def restore_stack(stack: torch.Tensor, taps_fn: Callable, flow_fn: Optional[Call
                 xk = sections_to_input(cache.get(k), None, 0)
                 # input_sff is a gray section replicated x3 (inference.py:129-131): its three warped planes are identical and
                 # PIL's 'L' of an R = G = B triple is R, so one plane is warped and stitched (a third of the bytes, same bits)
-                warped = warp(xk[:, :1], flow_fn(k, xk, interp))
-                warp_stitch(warped, interp, out=(local["warped"][i:i + 1], local["stitch"][i:i + 1]))
+                warp_and_stitch(xk[:, :1].contiguous(), flow_fn(k, xk, interp), interp,
+                                out=(local["warped"][i:i + 1], local["stitch"][i:i + 1]))
             if to_host:
                 done = torch.cuda.Event()
                 done.record()

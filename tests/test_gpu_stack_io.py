@@ -161,3 +161,24 @@ def test_section_gatherer_peer_writes_on_two_gpus():
         p.join(timeout=60)
     assert all(r[1] for r in res), res
     print("SectionGatherer mode:", res[0][2], res[0][3])
+
+
+@pytest.mark.parametrize("C,H,W,kind", [(1, 64, 128, "fold"), (3, 64, 128, "fold"), (3, 40, 64, "noise"), (1, 34, 50, "noise"), (3, 256, 256, "fold")])
+def test_warp_and_stitch_fused_equals_the_two_steps(C, H, W, kind):
+    """The stitch assembly as the warp kernel's epilogue == SpatialTransformation followed by warp_stitch, bit for bit
+    (TMA path, its global-gather tiles on a rough flow, and the scratch-image fall-back for W % 4 != 0)."""
+    r = np.random.default_rng(H + W + C)
+    moving = torch.from_numpy(r.random((2, C, H, W), dtype=np.float32)).cuda()
+    moving[:, :, 10:14, :] = 0.003                                          # < 2/255 after the cast: taken from the interpolation
+    if kind == "fold":
+        f = synth.random_fold_flow(H, W, 555)[0]
+    else:
+        f = synth.noise_flow(H, W, 6.0)
+    flow = torch.from_numpy(np.ascontiguousarray(f.transpose(2, 0, 1))[None]).cuda().expand(2, 2, H, W).contiguous().permute(0, 2, 3, 1)
+    interp = torch.from_numpy(r.integers(0, 256, (2, H, W), dtype=np.uint8)).cuda()
+    warped = pkg.SpatialTransformation(True)(moving, flow)
+    g0, s0 = pkg.warp_stitch(warped, interp)
+    g1, s1 = pkg.warp_and_stitch(moving, flow, interp)
+    assert torch.equal(g0, g1) and torch.equal(s0, s1)
+    _, s2 = pkg.warp_and_stitch(moving, flow, interp, want_gray=False)
+    assert torch.equal(s2, s0)
