@@ -433,3 +433,33 @@ def test_persistent_kernels_are_run_to_run_deterministic():
         else:
             for a, b, name in zip(ref, cur, ("out", "grad_vertical", "grad_horizontal")):
                 assert torch.equal(a, b), f"{name} differs between two launches on identical inputs"
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 1001, 1004), (3, 509, 516)])
+def test_persistent_kernels_on_ragged_large_shapes(B, H, W):
+    """Sizes that take the persistent kernels but are no multiple of their tiles (8 rows / 32 columns; the last CTA tile has
+    partially and fully out-of-image warp tiles): one-hot taps make the forward an exact gather and the tap gradients
+    plain channel sums of g * shifted input."""
+    dev = "cuda"
+    C = 3
+    torch.manual_seed(6)
+    x = torch.rand((B, C, H + 50, W + 50), device=dev)
+    fy, fx, v1, h1 = _one_hot_taps(B, H, W, 31, dev)
+    g = torch.randn((B, C, H, W), device=dev)
+    out, _, gv, gh = _bwd(x, v1, h1, g, need_input=False)
+    yy = torch.arange(H, device=dev).view(1, 1, H, 1) + fy
+    xx = torch.arange(W, device=dev).view(1, 1, 1, W) + fx
+    flat = (yy * (W + 50) + xx).expand(B, C, H, W).reshape(B, C, -1)
+    assert torch.equal(out, x.reshape(B, C, -1).gather(2, flat).reshape(B, C, H, W))
+    for f in (0, 17, 50):
+        yy = torch.arange(H, device=dev).view(1, 1, H, 1) + f
+        flat = (yy * (W + 50) + (torch.arange(W, device=dev).view(1, 1, 1, W) + fx)).expand(B, C, H, W).reshape(B, C, -1)
+        exp_v = (g * x.reshape(B, C, -1).gather(2, flat).reshape(B, C, H, W)).sum(1)
+        assert (gv[:, f] - exp_v).abs().max().item() <= 1e-5
+        flat = ((torch.arange(H, device=dev).view(1, 1, H, 1) + fy) * (W + 50) + torch.arange(W, device=dev).view(1, 1, 1, W) + f).expand(B, C, H, W).reshape(B, C, -1)
+        exp_h = (g * x.reshape(B, C, -1).gather(2, flat).reshape(B, C, H, W)).sum(1)
+        assert (gh[:, f] - exp_h).abs().max().item() <= 1e-5
+    # untouched guard band: the kernels must not write outside [B,51,H,W] / [B,C,H,W] (checked by the allocator's neighbours
+    # indirectly; here: a second run gives identical bits)
+    out2, _, gv2, gh2 = _bwd(x, v1, h1, g, need_input=False)
+    assert torch.equal(out, out2) and torch.equal(gv, gv2) and torch.equal(gh, gh2)
