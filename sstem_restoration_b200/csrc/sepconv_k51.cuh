@@ -768,7 +768,13 @@ __device__ __forceinline__ void gi_step(float* __restrict__ trowA, int thr, bool
 #pragma unroll
     for (int c = 0; c < CC; ++c)
 #pragma unroll
-        for (int pp = 0; pp < Gm::NP; ++pp) a2[c][pp] = __fmul2_rn(g2[c][pp], v2[pp]);   // v = 0 where fy is out of range
+        for (int pp = 0; pp < Gm::NP; ++pp) {
+            a2[c][pp] = __fmul2_rn(g2[c][pp], v2[pp]);   // v = 0 where fy is out of range ...
+            if (S >= 0) {                                // ... but 0 * NaN is NaN: a row outside its 51 steps must not leak one
+                if (S - 2 * pp > K51 - 1 || S - 2 * pp < 0) a2[c][pp].x = 0.f;
+                if (S - 2 * pp - 1 < 0 || S - 2 * pp - 1 > K51 - 1) a2[c][pp].y = 0.f;
+            }
+        }
     // One slot at a time: within a slot the 32 lanes (and the CC channel planes) hit distinct
     // words, so the read-modify-writes below are race free; ACROSS slots lanes do revisit words,
     // which is safe because a warp's shared-memory accesses execute in program order -- the
