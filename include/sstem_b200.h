@@ -161,6 +161,13 @@ int sstem_warp_forward(const float* moving, const float* flow, const int64_t flo
                        int64_t batch, int64_t channels, int64_t h, int64_t w,
                        int32_t out_layout, void* stream);
 
+/* Backward of sstem_warp_forward (NCHW): the gradients autograd derives through the reference's ATen ops
+ * (image_warp_torch.py:32-95; no reference call site needs them).  grad_out [B,C,H,W]; grad_moving [B,C,H,W] (nullable;
+ * zero-filled here, then accumulated with atomics: the order of the <= 4 x neighbours adds on an element may vary);
+ * grad_flow [B,H,W,2] CONTIGUOUS (nullable). */
+int sstem_warp_backward(const float* moving, const float* flow, const int64_t flow_strides[4], const float* grad_out,
+                        float* grad_moving, float* grad_flow, int64_t B, int64_t C, int64_t H, int64_t W, void* stream);
+
 /* pixel type of the numpy-semantics warp input */
 #define SSTEM_PIX_U8  0
 #define SSTEM_PIX_F32 1

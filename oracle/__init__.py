@@ -412,3 +412,44 @@ def warp_stitch_restated(warped, img_interp):
     mask[gray < 2] = 0
     stitch = (img_interp * (1 - mask) + gray * mask).astype(np.uint8)
     return gray, stitch
+
+
+def warp_torch_backward_restated(moving, flow, grad_out):
+    """Gradients of SpatialTransformation.forward (image_warp_torch.py:32-95) w.r.t. the moving image and the flow, as
+    autograd derives them through the reference's ATen ops (test oracle; float64 accumulation):
+
+      out = wa*Ia + wb*Ib + wc*Ic + wd*Id,  wa = dx*dy, wb = dx*(1-dy), wc = (1-dx)*dy, wd = (1-dx)*(1-dy),
+      dx = x1_clamped - x, dy = y1_clamped - y  (floor / clamp / the gather indices carry no gradient), so
+      d out / d fx = -(d out / d dx) = dy*(Ic - Ia) + (1-dy)*(Id - Ib),   d out / d fy = dx*(Ib - Ia) + (1-dx)*(Id - Ic),
+      d out / d I(y,x) = the weight of every tap that reads it (taps in the 1-px zero border give nothing).
+
+    moving [B,C,H,W], flow [B,H,W,2], grad_out [B,C,H,W] -> (grad_moving [B,C,H,W], grad_flow [B,H,W,2]) float32.
+    Pinned against the reference's own autograd by tests/golden/warp_torch_grad_ref.npz."""
+    moving = _f32(moving)
+    flow = np.asarray(flow, dtype=np.float32)
+    g = np.asarray(grad_out, dtype=np.float64)
+    B, C, H, W = moving.shape
+    one = np.float32(1.0)
+    jj = np.arange(W, dtype=np.float32)[None, None, :]
+    ii = np.arange(H, dtype=np.float32)[None, :, None]
+    x = (flow[..., 0] + jj) + one
+    y = (flow[..., 1] + ii) + one
+    x0 = np.clip(np.floor(x).astype(np.int64), 0, W + 1); x1 = np.clip(np.floor(x).astype(np.int64) + 1, 0, W + 1)
+    y0 = np.clip(np.floor(y).astype(np.int64), 0, H + 1); y1 = np.clip(np.floor(y).astype(np.int64) + 1, 0, H + 1)
+    dx = (x1.astype(np.float32) - x).astype(np.float64)
+    dy = (y1.astype(np.float32) - y).astype(np.float64)
+    wa, wb, wc, wd = dx * dy, dx * (1 - dy), (1 - dx) * dy, (1 - dx) * (1 - dy)
+    pad = np.zeros((B, C, H + 2, W + 2), np.float64)
+    pad[:, :, 1:-1, 1:-1] = moving
+    gpad = np.zeros_like(pad)
+    gflow = np.zeros((B, H, W, 2), np.float64)
+    bi = np.arange(B)[:, None, None] + np.zeros((B, H, W), np.int64)
+    for c in range(C):
+        pc = pad[:, c]
+        Ia, Ib, Ic, Id = pc[bi, y0, x0], pc[bi, y1, x0], pc[bi, y0, x1], pc[bi, y1, x1]
+        gc = g[:, c]
+        gflow[..., 0] += gc * (dy * (Ic - Ia) + (1 - dy) * (Id - Ib))
+        gflow[..., 1] += gc * (dx * (Ib - Ia) + (1 - dx) * (Id - Ic))
+        for w, yy, xx in ((wa, y0, x0), (wb, y1, x0), (wc, y0, x1), (wd, y1, x1)):
+            np.add.at(gpad[:, c], (bi, yy, xx), w * gc)
+    return gpad[:, :, 1:-1, 1:-1].astype(np.float32), gflow.astype(np.float32)

@@ -36,7 +36,7 @@ WARP_NEAREST = 1
 #: every symbol include/sstem_b200.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = (
     "sstem_sepconv_forward", "sstem_sepconv_backward", "sstem_interp_tail_forward", "sstem_interp_tail_backward",
-    "sstem_warp_forward", "sstem_image_warp", "sstem_sff_degrade", "sstem_sff_contrast",
+    "sstem_warp_forward", "sstem_warp_backward", "sstem_image_warp", "sstem_sff_degrade", "sstem_sff_contrast",
     "sstem_sections_to_input", "sstem_prediction_to_u8", "sstem_warp_stitch_u8", "sstem_warp_stitch_forward",
     "sstem_taps_tiled_elems", "sstem_taps_to_tiled", "sstem_sepconv_forward_tiled",
     "sstem_sepconv_forward_detect", "sstem_sepconv_backward_detect",
@@ -74,6 +74,8 @@ def load() -> ctypes.CDLL:
         lib.sstem_interp_tail_backward.restype = ctypes.c_int
         lib.sstem_warp_forward.argtypes = [_c_p, _c_p, ctypes.POINTER(_c_i64), _c_p, _c_i64, _c_i64, _c_i64, _c_i64, _c_i32, _c_p]
         lib.sstem_warp_forward.restype = ctypes.c_int
+        lib.sstem_warp_backward.argtypes = [_c_p, _c_p, ctypes.POINTER(_c_i64), _c_p, _c_p, _c_p, _c_i64, _c_i64, _c_i64, _c_i64, _c_p]
+        lib.sstem_warp_backward.restype = ctypes.c_int
         lib.sstem_image_warp.argtypes = [_c_p, _c_i32, _c_p, _c_p, _c_p, _c_i64, _c_i64, _c_i64, _c_i64, _c_i32, _c_p]
         lib.sstem_image_warp.restype = ctypes.c_int
         lib.sstem_sff_degrade.argtypes = [_c_p] * 7 + [_c_i64] * 4 + [_c_p]

@@ -641,6 +641,78 @@ extern "C" int sstem_warp_forward(const float* moving, const float* flow, const 
     return finish_launch();
 }
 
+// ---- backward of the torch-semantics warp ----------------------------------------------------------------------------
+// The reference's SpatialTransformation is differentiable through its ATen ops (image_warp_torch.py:32-95); no reference
+// call site uses that (main_fusion.py:227-235 runs it under no_grad / detach), so this is a plain one-thread-per-pixel
+// kernel, not a tuned one.  With out = wa Ia + wb Ib + wc Ic + wd Id, wa = dx dy, wb = dx (1-dy), wc = (1-dx) dy,
+// wd = (1-dx)(1-dy), dx = x1_clamped - x, dy = y1_clamped - y (floor, clamp and the gather indices carry no gradient):
+//   d out / d fx = dy (Ic - Ia) + (1-dy) (Id - Ib),   d out / d fy = dx (Ib - Ia) + (1-dx) (Id - Ic),
+//   d out / d I(tap) = the tap's weight (scattered with atomics; taps in the 1-px zero border give nothing).
+namespace sstem {
+__global__ void __launch_bounds__(256)
+warp_torch_backward_kernel(const float* __restrict__ moving, const float* __restrict__ flow,
+                           int64_t fs_b, int64_t fs_h, int64_t fs_w, int64_t fs_c, const float* __restrict__ grad_out,
+                           float* __restrict__ grad_moving, float* __restrict__ grad_flow, int C, int H, int W, int64_t total) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int j = (int)(idx % W), i = (int)((idx / W) % H);
+    const int64_t b = idx / ((int64_t)W * H);
+    const float* fp = flow + b * fs_b + (int64_t)i * fs_h + (int64_t)j * fs_w;
+    const float fx = __ldg(fp), fy = __ldg(fp + fs_c);
+    const BilinearTap t = torch_tap(fx, fy, i, j, H, W);
+    // dx, dy exactly as torch_tap forms them
+    const float x = __fadd_rn(__fadd_rn(fx, (float)j), 1.0f), y = __fadd_rn(__fadd_rn(fy, (float)i), 1.0f);
+    const float dx = __fsub_rn((float)t.x1, x), dy = __fsub_rn((float)t.y1, y);
+    const float ex = __fsub_rn(1.0f, dx), ey = __fsub_rn(1.0f, dy);
+    const int xa = t.x0 - 1, xb = t.x1 - 1, ya = t.y0 - 1, yb = t.y1 - 1;
+    const bool vxa = (unsigned)xa < (unsigned)W, vxb = (unsigned)xb < (unsigned)W;
+    const bool vya = (unsigned)ya < (unsigned)H, vyb = (unsigned)yb < (unsigned)H;
+    const int64_t plane = (int64_t)H * W;
+    float gfx = 0.f, gfy = 0.f;
+    for (int c = 0; c < C; ++c) {
+        const int64_t pb = (b * C + c) * plane;
+        const float g = __ldg(grad_out + pb + (int64_t)i * W + j);
+        if (grad_flow) {
+            const float* im = moving + pb;
+            const float Ia = (vya && vxa) ? __ldg(im + (int64_t)ya * W + xa) : 0.f, Ib = (vyb && vxa) ? __ldg(im + (int64_t)yb * W + xa) : 0.f;
+            const float Ic = (vya && vxb) ? __ldg(im + (int64_t)ya * W + xb) : 0.f, Id = (vyb && vxb) ? __ldg(im + (int64_t)yb * W + xb) : 0.f;
+            gfx += g * (dy * (Ic - Ia) + ey * (Id - Ib));
+            gfy += g * (dx * (Ib - Ia) + ex * (Id - Ic));
+        }
+        if (grad_moving) {
+            float* gm = grad_moving + pb;
+            if (vya && vxa) atomicAdd(gm + (int64_t)ya * W + xa, t.wa * g);
+            if (vyb && vxa) atomicAdd(gm + (int64_t)yb * W + xa, t.wb * g);
+            if (vya && vxb) atomicAdd(gm + (int64_t)ya * W + xb, t.wc * g);
+            if (vyb && vxb) atomicAdd(gm + (int64_t)yb * W + xb, t.wd * g);
+        }
+    }
+    if (grad_flow) {
+        grad_flow[2 * idx] = gfx;
+        grad_flow[2 * idx + 1] = gfy;
+    }
+}
+}  // namespace sstem
+
+extern "C" int sstem_warp_backward(const float* moving, const float* flow, const int64_t flow_strides[4], const float* grad_out,
+                                   float* grad_moving, float* grad_flow, int64_t B, int64_t C, int64_t H, int64_t W, void* stream) {
+    if (!moving || !flow || !flow_strides || !grad_out || (!grad_moving && !grad_flow)) return SSTEM_E_NULL;
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || H > (1 << 24) || W > (1 << 24) || H * W > INT32_MAX) return SSTEM_E_SHAPE;
+    if (!aligned4(moving) || !aligned4(flow) || !aligned4(grad_out) || !aligned4(grad_moving) || !aligned4(grad_flow)) return SSTEM_E_ALIGN;
+    DeviceGuard guard(grad_moving ? (const void*)grad_moving : (const void*)grad_flow);
+    if (guard.err) return guard.err;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (grad_moving) {
+        cudaError_t e = cudaMemsetAsync(grad_moving, 0, (size_t)(B * C * H * W) * sizeof(float), s);
+        if (e != cudaSuccess) return (int)e;
+    }
+    const int64_t total = B * H * W;
+    warp_torch_backward_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(moving, flow, flow_strides[0], flow_strides[1], flow_strides[2],
+                                                                             flow_strides[3], grad_out, grad_moving, grad_flow, (int)C, (int)H, (int)W, total);
+    count_launch();
+    return finish_launch();
+}
+
 extern "C" int sstem_warp_stitch_u8(const float* warped, const uint8_t* interp, uint8_t* gray_out, uint8_t* stitch_out,
                                     int64_t B, int64_t C, int64_t H, int64_t W, void* stream);
 

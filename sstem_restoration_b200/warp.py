@@ -53,17 +53,34 @@ def _warp_launch(moving, flow, nhwc_memory):
 
 
 class _WarpFunction(torch.autograd.Function):
-    """Only used when a gradient could be requested: its backward explains why there is none."""
+    """Differentiable like the reference's module (its ATen ops carry autograd: image_warp_torch.py:32-95): gradients
+    w.r.t. the moving image (scatter of the tap weights) and the flow, through ``sstem_warp_backward``."""
 
     @staticmethod
     def forward(ctx, moving, flow, nhwc_memory):
+        ctx.save_for_backward(moving, flow)
         return _warp_launch(moving, flow, nhwc_memory)
 
     @staticmethod
     def backward(ctx, grad):
-        raise NotImplementedError(
-            "SpatialTransformation backward is not provided: no reference call site differentiates "
-            "through the warp (sff_scripts_fusion/main_fusion.py:227-235 runs it under no_grad/detach)")
+        moving, flow = ctx.saved_tensors
+        need_m, need_f = ctx.needs_input_grad[:2]
+        if not (need_m or need_f):
+            return None, None, None
+        B, C, H, W = moving.shape
+        if grad.is_cuda == False:
+            raise NotImplementedError()
+        grad = grad.to(torch.float32).contiguous()             # [B,C,H,W] (a permuted NHWC view becomes NCHW here)
+        gm = torch.empty_like(moving) if need_m else None
+        gf = torch.empty((B, H, W, 2), dtype=torch.float32, device=moving.device) if need_f else None
+        if moving.numel():
+            strides = (ctypes.c_int64 * 4)(*flow.stride())
+            code = _lib.load().sstem_warp_backward(
+                moving.data_ptr(), flow.data_ptr(), strides, grad.data_ptr(), gm.data_ptr() if need_m else None,
+                gf.data_ptr() if need_f else None, B, C, H, W, _stream_ptr(moving.device))
+            if code:
+                _lib.check(code, "sstem_warp_backward")
+        return gm, gf, None
 
 
 class SpatialTransformation(nn.Module):

@@ -76,12 +76,38 @@ def test_spatial_transformation_exact_properties_at_full_size(H, W):
     assert torch.equal(got, expect)
 
 
-def test_spatial_transformation_backward_is_refused():
+def test_spatial_transformation_backward_matches_reference_autograd(golden_dir):
+    """Gradients w.r.t. the moving image and the flow against autograd through the reference's own module
+    (tests/golden/warp_torch_grad_ref.npz) and the oracle restatement; planar-strided flow view and NHWC memory too."""
+    from sstem_restoration_b200 import SpatialTransformation
+    from tests.golden.make_warp_grad_golden import upstream
+    ref = np.load(os.path.join(golden_dir, "warp_torch_grad_ref.npz"))
+    for name, (mv, fl) in cases.warp_torch_cases().items():
+        if name + "_gm" not in ref:
+            continue
+        g = torch.from_numpy(upstream(name, mv.shape)).cuda()
+        for variant in ("interleaved", "planar_view", "nhwc"):
+            m = torch.from_numpy(mv).cuda().requires_grad_(True)
+            if variant == "planar_view":
+                base = torch.from_numpy(np.ascontiguousarray(fl.transpose(0, 3, 1, 2))).cuda().requires_grad_(True)
+                f = base.permute(0, 2, 3, 1)
+            else:
+                base = f = torch.from_numpy(fl).cuda().requires_grad_(True)
+            out = SpatialTransformation(True, nhwc_memory=(variant == "nhwc"))(m, f)
+            out.backward(g)
+            gf = base.grad.permute(0, 2, 3, 1) if variant == "planar_view" else base.grad
+            for got, want in ((m.grad, ref[name + "_gm"]), (gf, ref[name + "_gf"])):
+                assert np.abs(got.cpu().numpy() - want).max() <= 2e-5 * max(1.0, np.abs(want).max()), (name, variant)
+        om, of = oracle.warp_torch_backward_restated(mv, fl, g.cpu().numpy())
+        assert np.abs(m.grad.cpu().numpy() - om).max() <= 2e-5 * max(1.0, np.abs(om).max())
+
+
+def test_spatial_transformation_backward_only_what_is_needed():
     from sstem_restoration_b200 import SpatialTransformation
     moving = torch.rand((1, 1, 8, 8), device="cuda", requires_grad=True)
     out = SpatialTransformation(True)(moving, torch.zeros((1, 8, 8, 2), device="cuda"))
-    with pytest.raises(NotImplementedError):
-        out.sum().backward()
+    out.sum().backward()
+    assert torch.equal(moving.grad, torch.ones_like(moving))       # identity flow: every pixel is its own (only) tap
 
 
 # ---------------------------------------------------------------- numpy image_warp

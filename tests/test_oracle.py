@@ -244,3 +244,16 @@ def test_warp_stitch_restatement_matches_pillow():
         assert np.array_equal(gray, pil) and np.array_equal(stitch, want)
         if kind == "gray":
             assert np.array_equal(gray, w8[0])
+
+
+def test_warp_backward_restatement_matches_reference_autograd(golden_dir):
+    """The gradient formulas of oracle.warp_torch_backward_restated against autograd through the reference's own
+    SpatialTransformation (tests/golden/make_warp_grad_golden.py)."""
+    ref = np.load(os.path.join(golden_dir, "warp_torch_grad_ref.npz"))
+    from tests.golden.make_warp_grad_golden import upstream
+    for name, (mv, fl) in cases.warp_torch_cases().items():
+        if name + "_gm" not in ref:
+            continue
+        gm, gf = oracle.warp_torch_backward_restated(mv, fl, upstream(name, mv.shape))
+        assert np.abs(gm - ref[name + "_gm"]).max() <= 2e-5 * max(1.0, np.abs(ref[name + "_gm"]).max()), name
+        assert np.abs(gf - ref[name + "_gf"]).max() <= 2e-5 * max(1.0, np.abs(ref[name + "_gf"]).max()), name
