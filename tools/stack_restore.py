@@ -1,22 +1,16 @@
-"""BASELINE config 5 in miniature: restore a synthetic EM stack, sharded by section pair.
+"""BASELINE config 5 from the command line: restore a synthetic EM stack, sharded by section pair.
 
     python tools/stack_restore.py --sections 20 --size 2048            # 1 GPU
     torchrun --nproc-per-node 8 tools/stack_restore.py --sections 100 --size 4096
 
-Target k (interior section) is interpolated from sections k-1 and k+1 exactly as the reference's
-tail does (sff_scripts_interp/inference.py:69-89 -> model_interp.py:90-97): two sepconv calls on the
-replicate-padded neighbours + add + channel mean -- by default as ONE launch (interpolation_tail),
-with uint8 sections on the wire (sections_to_input / prediction_to_uint8 replace inference.py:69-88's
-host-side /255, x3 replicate and *255 cast); the degraded section k itself is flow-warped
-(sff_scripts_fusion/inference.py:149-150).  Taps and flows are synthetic (the KPN / flow net are out
-of scope).  Ranks own contiguous target ranges (shard.shard_range), never communicate while
-computing, and the restored sections are gathered to rank 0 at the end (the path's only collective).
-"""
+A thin wrapper over `sstem_restoration_b200.restore_stack` (the package API; `bench.py` measures the same call as
+`extra.configs.c5_stack`): target k is interpolated from sections k-1 and k+1 (sff_scripts_interp/inference.py:69-89 ->
+model_interp.py:90-97, one fused launch), section k is flow-warped and stitched (sff_scripts_fusion/inference.py:149-171,
+one fused launch), uint8 on the wire.  Taps and flow are synthetic: the KPN / flow net are out of scope."""
 import argparse
 import json
 import os
 import sys
-import time
 
 import numpy as np
 import torch
@@ -31,10 +25,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--sections", type=int, default=20)
     ap.add_argument("--size", type=int, default=2048)
-    ap.add_argument("--gray", default="detect", choices=["off", "assert", "detect"])
-    ap.add_argument("--unfused", action="store_true",
-                    help="float sections on the wire and the reference's op-by-op tail (2 pads + 2 sepconvs + add + mean) "
-                         "instead of uint8 sections + sections_to_input + interpolation_tail + prediction_to_uint8")
+    ap.add_argument("--to-host", action="store_true", help="every rank downloads its own restored sections into pinned memory")
     args = ap.parse_args()
     rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     torch.cuda.set_device(local)
@@ -43,53 +34,23 @@ def main():
         os.environ.setdefault("NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=dev)
     H = W = args.size
-    targets = shard.stack_targets(args.sections)
-    lo, hi = shard.shard_range(len(targets), rank, world)
-    pkg.set_gray_replicated(args.gray)
-    sep = pkg.SeparableConvolution.apply
-    warp = pkg.SpatialTransformation(True)
-    pad = torch.nn.ReplicationPad2d(25)
     gen = torch.Generator(device=dev).manual_seed(4321 + rank)
-    # synthetic taps / flow, reused for every pair (their values do not affect speed)
     taps = [torch.softmax(torch.randn((1, 51, H, W), device=dev, generator=gen), 1) for _ in range(4)]
     flow_np, _ = synth.random_fold_flow(H, W, 555)
     flow = torch.from_numpy(np.ascontiguousarray(flow_np.transpose(2, 0, 1))[None]).to(dev).permute(0, 2, 3, 1)
-    # the stack as it sits on the host: uint8 sections in pinned memory (a stand-in for decoded PNGs)
     tile = synth.em_section(min(H, 1024), min(W, 1024), 0)
-    base = torch.from_numpy(np.tile(tile, (H // tile.shape[0], W // tile.shape[1]))).pin_memory()
-    need = sorted({k for t in targets[lo:hi] for k in t})
-    host = {k: torch.roll(base, shifts=7 * k, dims=1).pin_memory() for k in need}
-
-    def restore(ka, k, kb):
-        """One target: sections k-1 / k+1 -> interpolated section k; section k itself -> flow-corrected; blend."""
-        up = {i: host[i].to(dev, non_blocking=True) for i in (ka, k, kb)}                 # 1 byte per pixel over PCIe
-        x = pkg.sections_to_input(up[ka], up[kb], 0)                                        # [1,6,H,W] float, /255, x3
-        if args.unfused:
-            y = sep(pad(x[:, 3:6]), taps[0], taps[1]) + sep(pad(x[:, :3]), taps[2], taps[3])
-            interp = torch.mean(y, dim=1, keepdim=True)
-        else:
-            interp = pkg.interpolation_tail(x[:, :3], x[:, 3:6], taps[2], taps[3], taps[0], taps[1])
-        xk = pkg.sections_to_input(up[k], up[k], 0)[:, :3].contiguous()
-        warped = warp(xk, flow)                                                             # correction-module warp of section k
-        return pkg.prediction_to_uint8(0.5 * (interp + warped[:, :1]), 0)                   # [1,H,W] uint8
-
-    restored = torch.empty((hi - lo, H, W), dtype=torch.uint8, device=dev)
-    with torch.no_grad():                               # warm-up: first-launch setup, allocator, NCCL communicator
-        if hi > lo:
-            restore(*targets[lo])
-        if world > 1:
-            n_w = shard.shard_range(world, rank, world)
-            shard.gather_sections(torch.zeros((n_w[1] - n_w[0], 8, 8), dtype=torch.uint8, device=dev), world, dst=0)
-    torch.cuda.synchronize()
+    base = torch.from_numpy(np.tile(tile, (H // tile.shape[0], W // tile.shape[1])))
+    stack = torch.stack([torch.roll(base, shifts=7 * k, dims=1) for k in range(args.sections)]).pin_memory()
+    pkg.set_gray_replicated("assert")
+    kw = dict(rank=rank, world_size=world, dst=0, device=dev, to_host=args.to_host)
+    pkg.restore_stack(stack[:4], lambda k, x: taps, lambda k, xk, interp: flow, device=dev)          # warm-up
     if world > 1:
+        shard.gather_sections(torch.zeros((1, 8, 8), dtype=torch.uint8, device=dev), world, dst=0)
         dist.barrier()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n0 = pkg.launch_count()
     e0.record()
-    with torch.no_grad():
-        for n, t in enumerate(targets[lo:hi]):
-            restored[n] = restore(*t)[0]
-    full = shard.gather_sections(restored, len(targets), dst=0) if world > 1 else restored
+    out = pkg.restore_stack(stack, lambda k, x: taps, lambda k, xk, interp: flow, **kw)
     e1.record()
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
@@ -97,12 +58,10 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     if rank == 0:
         t = float(ms.item()) * 1e-3
-        print(json.dumps({"workload": f"stack restoration, {args.sections} sections {H}x{W}, {len(targets)} targets", "n_gpus": world,
-                          "seconds": round(t, 4), "sections_per_s": round(len(targets) / t, 2),
-                          "mpix_per_s": round(len(targets) * H * W / t / 1e6, 1), "gray_mode": args.gray,
-                          "path": "unfused float" if args.unfused else "uint8 wire + fused tail",
-                          "gathered": list(full.shape), "gathered_dtype": str(full.dtype),
-                          "kernel_launches_rank0": pkg.launch_count() - n0}))
+        n = out["stats"]["targets"]
+        print(json.dumps({"workload": f"stack restoration, {args.sections} sections {H}x{W}, {n} targets", "n_gpus": world,
+                          "seconds": round(t, 4), "sections_per_s": round(n / t, 2), "mpix_per_s": round(n * H * W / t / 1e6, 1),
+                          "outputs": {k: list(v.shape) for k, v in out.items() if k != "stats" and v is not None}, "stats": out["stats"]}))
     if world > 1:
         dist.destroy_process_group()
 
