@@ -289,6 +289,30 @@ int sstem_sepconv_forward_tiled(const float* input, const float* vertical_tiled,
                                 int32_t K, uint32_t flags, void* stream);
 
 /*
+ * Tap producer (producer side): the last two layers of IFNet._kernel_module,
+ *     nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) -> nn.Conv2d(51, 51, 3, 1, 1)
+ * (sff_scripts_interp/model/model_interp.py:18, 130-137; four instances per forward, :34-37, :86-89), as one sm_100a
+ * kernel: tcgen05 TF32 implicit GEMM (torch runs this layer in TF32 through cuDNN by default), the bilinear upsample
+ * folded into the operand producer, the result written [B,cout,H,W] or directly tile-major (SSTEM_TAPCONV_TILED, the
+ * layout of sstem_sepconv_forward_tiled; cout must then be 51).
+ *
+ *   x       [B, cin, h, w]      cin <= 56
+ *   weight  [cout, cin, 3, 3]   cout <= 64 (torch's Conv2d.weight); packed once by sstem_tap_conv3x3_pack_weights into
+ *                               sstem_tap_conv3x3_packed_elems() floats ([tap][cin chunk of 4][64][4], rounded to TF32)
+ *   bias    [cout] or NULL
+ *   out     [B, cout, H, W] or tiled; (H, W) = (2h, 2w) with SSTEM_TAPCONV_UPSAMPLE2X, else (h, w)
+ *
+ * Arithmetic: operands rounded to TF32 (round-to-nearest), products accumulated in fp32 -- the reference layer's own
+ * precision class; tests hold it to the TF32 bound against an fp64 restatement, not to bit equality with cuDNN.
+ */
+#define SSTEM_TAPCONV_UPSAMPLE2X 1u
+#define SSTEM_TAPCONV_TILED 2u
+int64_t sstem_tap_conv3x3_packed_elems(void);
+int sstem_tap_conv3x3_pack_weights(const float* weight, float* packed, int32_t cin, int32_t cout, void* stream);
+int sstem_tap_conv3x3(const float* x, const float* packed_weight, const float* bias, float* out,
+                      int64_t B, int32_t cin, int32_t cout, int64_t h, int64_t w, uint32_t flags, void* stream);
+
+/*
  * Gray x3 detection on the device, without a host round trip.  Every reference caller feeds sepconv a grayscale section
  * replicated x3 (sff_scripts_interp/data/data_provider.py:136-137, inference.py:71-77): identical channel planes, for which
  * one plane of work gives all outputs (SSTEM_SEPCONV_GRAY_REPLICATED).  These entry points decide that themselves:

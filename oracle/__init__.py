@@ -453,3 +453,48 @@ def warp_torch_backward_restated(moving, flow, grad_out):
         for w, yy, xx in ((wa, y0, x0), (wb, y1, x0), (wc, y0, x1), (wd, y1, x1)):
             np.add.at(gpad[:, c], (bi, yy, xx), w * gc)
     return gpad[:, :, 1:-1, 1:-1].astype(np.float32), gflow.astype(np.float32)
+
+
+def upsample2x_align_corners_restated(x, dtype=np.float64):
+    """``nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True)`` (sff_scripts_interp/model/model_interp.py:18)
+    the way ATen's upsample_bilinear2d computes it for float tensors: scale = (in - 1) / (out - 1) in float32, source index
+    = scale * dst (float32) cut to int, neighbour = + 1 unless that is past the last row / column, weights from the
+    fraction (float32); value = h0 * (w0 * a + w1 * b) + h1 * (w0 * c + w1 * d).  Indices and weights in float32 as ATen;
+    the blend in ``dtype`` (float64: ground truth for the TF32 bound; float32: comparable with the golden ``up`` to an ulp).
+    Pinned by tests/golden/tap_producer_ref.npz (made from the reference's own model on CPU)."""
+    x = np.asarray(x)
+    B, C, h, w = x.shape
+    H, W = 2 * h, 2 * w
+
+    def axis(n_in, n_out):
+        scale = np.float32(n_in - 1) / np.float32(n_out - 1) if n_out > 1 else np.float32(0)
+        r = (scale * np.arange(n_out, dtype=np.float32)).astype(np.float32)
+        i0 = r.astype(np.int64)
+        i1 = i0 + (i0 < n_in - 1)
+        l1 = (r - i0.astype(np.float32)).astype(np.float32)
+        l0 = (np.float32(1) - l1).astype(np.float32)
+        return i0, i1, l0.astype(dtype), l1.astype(dtype)
+
+    y0, y1, hy0, hy1 = axis(h, H)
+    x0, x1, wx0, wx1 = axis(w, W)
+    xd = x.astype(dtype)
+    top = wx0 * xd[:, :, y0][:, :, :, x0] + wx1 * xd[:, :, y0][:, :, :, x1]
+    bot = wx0 * xd[:, :, y1][:, :, :, x0] + wx1 * xd[:, :, y1][:, :, :, x1]
+    return hy0[:, None] * top + hy1[:, None] * bot
+
+
+def tap_conv3x3_restated(x, weight, bias=None, upsample=True, dtype=np.float64):
+    """The tail of ``IFNet._kernel_module`` (model_interp.py:130-137): [upsample x2 ->] ``Conv2d(cin, cout, 3, 1, 1)``
+    (cross-correlation, zero padding 1), accumulated in ``dtype``.  x [B,cin,h,w], weight [cout,cin,3,3], bias [cout]."""
+    up = upsample2x_align_corners_restated(x, dtype) if upsample else np.asarray(x).astype(dtype)
+    B, C, H, W = up.shape
+    wt = np.asarray(weight).astype(dtype)
+    pad = np.zeros((B, C, H + 2, W + 2), dtype)
+    pad[:, :, 1:-1, 1:-1] = up
+    out = np.zeros((B, wt.shape[0], H, W), dtype)
+    for dy in range(3):
+        for dx in range(3):
+            out += np.einsum("nc,bchw->bnhw", wt[:, :, dy, dx], pad[:, :, dy:dy + H, dx:dx + W], optimize=True)
+    if bias is not None:
+        out += np.asarray(bias).astype(dtype)[None, :, None, None]
+    return out

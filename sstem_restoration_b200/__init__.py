@@ -21,11 +21,13 @@ from .warp import SpatialTransformation, image_warp  # noqa: F401
 from .host import sepconv_forward_backward_host, join_host_pipeline  # noqa: F401
 from .stack_io import sections_to_input, prediction_to_uint8  # noqa: F401
 from .stack import restore_stack, warp_stitch, warp_and_stitch  # noqa: F401
+from .tapconv import tap_conv3x3, pack_tap_conv_weight, ModuleTapProducer  # noqa: F401
 from . import shard, synth, sff_sim  # noqa: F401
 
 __all__ = [
     "SeparableConvolution", "FunctionSepconv", "ModuleSepconv", "set_strict_order", "set_gray_replicated",
     "interpolation_tail", "ModuleInterpolationTail", "taps_to_tiled", "sepconv_forward_tiled",
     "SpatialTransformation", "image_warp", "sepconv_forward_backward_host", "join_host_pipeline", "SstemError", "launch_count", "fp32_peak_probe",
-    "sections_to_input", "prediction_to_uint8", "restore_stack", "warp_stitch", "warp_and_stitch", "shard", "synth", "sff_sim",
+    "sections_to_input", "prediction_to_uint8", "restore_stack", "warp_stitch", "warp_and_stitch",
+    "tap_conv3x3", "pack_tap_conv_weight", "ModuleTapProducer", "shard", "synth", "sff_sim",
 ]

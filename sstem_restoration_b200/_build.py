@@ -30,6 +30,7 @@ UNITS = [
     ("sepconv_k51_gi.cu", [], ""),
     ("sepconv_k51_tail.cu", [], ""),
     ("warp.cu", [], ""),
+    ("tapconv.cu", [], ""),
     ("sff_sim.cu", [], ""),
     ("stack_io.cu", [], ""),
     ("probe.cu", [], ""),

@@ -26,6 +26,8 @@ _c_p = ctypes.c_void_p
 SEPCONV_DEFAULT = 0
 SEPCONV_STRICT_ORDER = 1
 SEPCONV_GRAY_REPLICATED = 2
+TAPCONV_UPSAMPLE2X = 1
+TAPCONV_TILED = 2
 LAYOUT_NCHW = 0
 LAYOUT_NHWC = 1
 PIX_U8 = 0
@@ -40,6 +42,7 @@ EXPORTED_SYMBOLS = (
     "sstem_sections_to_input", "sstem_prediction_to_u8", "sstem_warp_stitch_u8", "sstem_warp_stitch_forward",
     "sstem_taps_tiled_elems", "sstem_taps_to_tiled", "sstem_sepconv_forward_tiled",
     "sstem_sepconv_forward_detect", "sstem_sepconv_backward_detect",
+    "sstem_tap_conv3x3_packed_elems", "sstem_tap_conv3x3_pack_weights", "sstem_tap_conv3x3",
     "sstem_fp32_peak_probe", "sstem_launch_count", "sstem_abi_version", "sstem_error_string",
 )
 
@@ -100,6 +103,12 @@ def load() -> ctypes.CDLL:
         lib.sstem_sepconv_forward_detect.restype = ctypes.c_int
         lib.sstem_sepconv_backward_detect.argtypes = [_c_p] * 7 + [_c_i64] * 4 + [_c_i32, _c_u32, _c_p, _c_p]
         lib.sstem_sepconv_backward_detect.restype = ctypes.c_int
+        lib.sstem_tap_conv3x3_packed_elems.argtypes = []
+        lib.sstem_tap_conv3x3_packed_elems.restype = _c_i64
+        lib.sstem_tap_conv3x3_pack_weights.argtypes = [_c_p, _c_p, _c_i32, _c_i32, _c_p]
+        lib.sstem_tap_conv3x3_pack_weights.restype = ctypes.c_int
+        lib.sstem_tap_conv3x3.argtypes = [_c_p, _c_p, _c_p, _c_p, _c_i64, _c_i32, _c_i32, _c_i64, _c_i64, _c_u32, _c_p]
+        lib.sstem_tap_conv3x3.restype = ctypes.c_int
         lib.sstem_fp32_peak_probe.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
         lib.sstem_fp32_peak_probe.restype = ctypes.c_int
         lib.sstem_launch_count.argtypes = []

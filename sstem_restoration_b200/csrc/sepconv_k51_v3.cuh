@@ -174,8 +174,11 @@ __device__ __forceinline__ void bwd3_step(unsigned pa, unsigned pa_last, const u
         gvp[pp] = SSTEM_BWD3_SPLIT ? make_float2(gva[pp].x + gvb[pp].x, gva[pp].y + gvb[pp].y) : gva[pp];
 }
 
+#ifndef SSTEM_BWD3_MINB
+#define SSTEM_BWD3_MINB 2
+#endif
 template <bool WV, bool WH, bool ACCUM>
-__global__ void __launch_bounds__(V3_WARPS * 32, 2)
+__global__ void __launch_bounds__(V3_WARPS * 32, SSTEM_BWD3_MINB)
 sepconv_bwd_taps_k51_v3_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_v,
                                const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_g,
                                float* __restrict__ gv, float* __restrict__ gh, int* __restrict__ next_tile_counter,

@@ -1,0 +1,382 @@
+// Tap producer (SURVEY 8f, N2 -- the producer side): the last layer pair of the reference's `_kernel_module`,
+//     nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True)  ->  nn.Conv2d(51, 51, 3, 1, 1)
+// (sff_scripts_interp/model/model_interp.py:18, 130-137; called four times per forward, :86-89), as ONE kernel that
+// reads the half-resolution activations, never materialises the upsampled tensor, and writes the taps either NCHW or
+// straight into the tile-major layout the consumer streams ([B][H/8][W/8][51][8][8], sstem_sepconv_forward_tiled).
+//
+// The reference runs this layer through cuDNN with torch's default `allow_tf32 = True`, i.e. in TF32 on the tensor
+// cores; so does this kernel, hand-written for sm_100a:
+//   * implicit GEMM per output tile of 16 rows x 8 columns: D[128 pixels x 64] += A_tap[128 x 56] * W_tap[64 x 56]^T for
+//     the nine taps, 7 K-steps of 8 each = 63 tcgen05.mma (kind::tf32, M = 128, N = 64), accumulator in TMEM
+//     (two stages of 64 columns, so the epilogue of tile i overlaps the MMAs of tile i + 1);
+//   * the A operand is never gathered per tap: the upsampled 18 x 10 input patch lives in shared memory ONCE, as
+//     [channel chunk of 4][patch pixel][4 channels] (16 bytes per pixel and chunk).  In the no-swizzle K-major
+//     canonical layout a core matrix is 8 rows x 16 bytes, contiguous: 8 neighbouring pixels of a patch row.  The
+//     descriptor of tap (dy, dx) is the same patch with its start address moved by (dy * 10 + dx) * 16 bytes,
+//     stride-byte-offset = one patch row (160 B), leading-byte-offset = one chunk (2880 B)
+//     (tools/microbench/umma_probe.cu checks exactly this encoding, shifted starts included);
+//   * the weights of all nine taps stay resident in shared memory for the life of the CTA (126 KB, one bulk copy);
+//   * warp roles: 4 epilogue warps (TMEM -> registers -> + bias -> global), 1 MMA warp (one lane issues), 6 producer
+//     warps (source window -> shared memory, bilinear blend with PyTorch's own index / weight expressions, round to
+//     TF32, write the patch); mbarriers between them, a persistent grid of one CTA per SM.
+// Shared memory bandwidth bounds the kernel (each MMA reads 4 KB of A and 2 KB of W for 65 536 FMAs); see DESIGN 4.11.
+#include <algorithm>
+
+#include "common.cuh"
+#include "tma.cuh"
+
+namespace sstem {
+namespace {
+
+constexpr int TC_MAXC = 56;                                // input channels, padded to chunks of 4 and K-steps of 8
+constexpr int TC_CHUNKS = TC_MAXC / 4;                     // 14
+constexpr int TC_N = 64;                                   // output channels, padded (UMMA N)
+constexpr int TC_TH = 16, TC_TW = 8;                       // output tile: 128 pixels = UMMA M
+constexpr int TC_PH = TC_TH + 2, TC_PW = TC_TW + 2, TC_NPIX = TC_PH * TC_PW;   // 18 x 10 = 180
+constexpr int TC_WIN_H = 11, TC_WIN_W = 7, TC_WIN_PIX = TC_WIN_H * TC_WIN_W;   // half-resolution source window
+constexpr unsigned TC_W_TAP_BYTES = TC_CHUNKS * TC_N * 16;                     // 14336
+constexpr unsigned TC_W_BYTES = 9 * TC_W_TAP_BYTES;                            // 129024
+constexpr unsigned TC_A_BYTES = TC_CHUNKS * TC_NPIX * 16;                      // 40320
+constexpr unsigned TC_WIN_BYTES = (TC_CHUNKS * TC_WIN_PIX * 16 + 127) / 128 * 128;         // 17280
+constexpr unsigned TC_OFF_A = TC_W_BYTES;
+constexpr unsigned TC_OFF_WIN = TC_OFF_A + 2 * TC_A_BYTES;
+constexpr unsigned TC_OFF_BIAS = TC_OFF_WIN + TC_WIN_BYTES;
+constexpr unsigned TC_OFF_BAR = TC_OFF_BIAS + TC_N * 4;
+constexpr unsigned TC_SMEM = TC_OFF_BAR + 128 + 128;       // + barriers + alignment slack = 227 456 (of 232 448)
+constexpr int TC_EPI_WARPS = 4, TC_PROD_WARPS = 6;
+constexpr int TC_THREADS = (TC_EPI_WARPS + 1 + TC_PROD_WARPS) * 32;            // 352
+constexpr int TC_PROD_THREADS = TC_PROD_WARPS * 32;                            // 192 >= 180 patch pixels
+constexpr unsigned TC_TMEM_COLS = 128;                     // two accumulator stages of 64 columns
+
+struct TapConvShape {
+    int B, cin, cout, h, w, H, W;                          // h, w: source; H, W: output (2h, 2w when upsampling)
+    int tiles_x, tiles_y, ntiles;
+    int k_steps;                                           // ceil(cin / 8)
+    float ry, rx;                                          // align_corners scales (in - 1) / (out - 1)
+};
+
+// a wait that cannot hang the device: a protocol error traps (the launch fails loudly) instead of spinning for ever
+__device__ __forceinline__ void tc_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) return;
+    const long long t0 = clock64();
+    for (;;) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return;
+        if (clock64() - t0 > 4000000000ll) __trap();       // ~2 s
+    }
+}
+__device__ __forceinline__ void tc_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_commit(unsigned bar) {   // arrives on `bar` when every MMA issued so far has completed
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint64_t tc_desc(unsigned addr, unsigned lbo, unsigned sbo) {
+    // K-major, no swizzle: start >> 4 | leading byte offset (next 16-byte K chunk) | stride byte offset (next 8 rows) | version 1
+    return (uint64_t)((addr >> 4) & 0x3fffu) | ((uint64_t)((lbo >> 4) & 0x3fffu) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3fffu) << 32) | ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ void tc_bulk_load(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ float to_tf32(float x) {        // round to nearest (the tensor core itself would truncate)
+    unsigned u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ void sts128(unsigned addr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128(unsigned addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
+template <bool UPS, bool TILED>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tap_conv3x3_kernel(const float* __restrict__ x, const float* __restrict__ wpacked, const float* __restrict__ bias,
+                   float* __restrict__ out, const TapConvShape sh) {
+    extern __shared__ __align__(128) unsigned char tc_smem_raw[];
+    const unsigned base = ((unsigned)__cvta_generic_to_shared(tc_smem_raw) + 127u) & ~127u;
+    unsigned char* gen = tc_smem_raw + (base - (unsigned)__cvta_generic_to_shared(tc_smem_raw));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // barriers: 0 weights, 1-2 a_full, 3-4 a_empty, 5-6 acc_full, 7-8 acc_empty; the TMEM base address after them
+    const unsigned bar = base + TC_OFF_BAR;
+    const unsigned b_w = bar, b_afull = bar + 8, b_aempty = bar + 24, b_accfull = bar + 40, b_accempty = bar + 56;
+    volatile unsigned* tmem_slot = reinterpret_cast<volatile unsigned*>(gen + TC_OFF_BAR + 96);
+
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b_w));
+        for (int s = 0; s < 2; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b_afull + 8 * s), "r"(TC_PROD_THREADS));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b_aempty + 8 * s));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b_accfull + 8 * s));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b_accempty + 8 * s), "r"(TC_EPI_WARPS * 32));
+        }
+        mbar_fence_init();
+    }
+    // zero both patches once (the chunks past cin and the pad pixels a tile never writes must be finite) and the bias pad
+    for (unsigned i = tid; i < 2 * TC_A_BYTES / 16; i += TC_THREADS) sts128(base + TC_OFF_A + i * 16, 0.f, 0.f, 0.f, 0.f);
+    for (unsigned i = tid; i < TC_WIN_BYTES / 16; i += TC_THREADS) sts128(base + TC_OFF_WIN + i * 16, 0.f, 0.f, 0.f, 0.f);
+    if (tid < TC_N) reinterpret_cast<float*>(gen + TC_OFF_BIAS)[tid] = (bias != nullptr && tid < sh.cout) ? bias[tid] : 0.f;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 0) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bar + 96), "n"(TC_TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tmem = *tmem_slot;
+
+    auto decode = [&](int t, int& b, int& Y0, int& X0) {
+        const int tx = t % sh.tiles_x, r = t / sh.tiles_x;
+        X0 = tx * TC_TW;
+        Y0 = (r % sh.tiles_y) * TC_TH;
+        b = r / sh.tiles_y;
+    };
+
+    if (warp < TC_EPI_WARPS) {
+        // ===================== epilogue: TMEM lanes 32 * warp .. + 31 = tile pixels (row 4 * warp + lane / 8, column lane % 8)
+        const float* sbias = reinterpret_cast<const float*>(gen + TC_OFF_BIAS);
+        const int r = warp * 4 + (lane >> 3), c = lane & 7;
+        const int64_t plane = (int64_t)sh.H * sh.W;
+        const int tiles_y8 = (sh.H + 7) / 8, tiles_x8 = (sh.W + 7) / 8;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < sh.ntiles; tile += gridDim.x, ++it) {
+            const int as = it & 1;
+            int b, Y0, X0;
+            decode(tile, b, Y0, X0);
+            tc_wait(b_accfull + 8 * as, (it >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            unsigned v[64];
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const unsigned ta = tmem + ((unsigned)(warp * 32) << 16) + as * TC_N + hh * 32;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                    "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                    : "=r"(v[hh*32+0]), "=r"(v[hh*32+1]), "=r"(v[hh*32+2]), "=r"(v[hh*32+3]), "=r"(v[hh*32+4]), "=r"(v[hh*32+5]),
+                      "=r"(v[hh*32+6]), "=r"(v[hh*32+7]), "=r"(v[hh*32+8]), "=r"(v[hh*32+9]), "=r"(v[hh*32+10]), "=r"(v[hh*32+11]),
+                      "=r"(v[hh*32+12]), "=r"(v[hh*32+13]), "=r"(v[hh*32+14]), "=r"(v[hh*32+15]), "=r"(v[hh*32+16]), "=r"(v[hh*32+17]),
+                      "=r"(v[hh*32+18]), "=r"(v[hh*32+19]), "=r"(v[hh*32+20]), "=r"(v[hh*32+21]), "=r"(v[hh*32+22]), "=r"(v[hh*32+23]),
+                      "=r"(v[hh*32+24]), "=r"(v[hh*32+25]), "=r"(v[hh*32+26]), "=r"(v[hh*32+27]), "=r"(v[hh*32+28]), "=r"(v[hh*32+29]),
+                      "=r"(v[hh*32+30]), "=r"(v[hh*32+31])
+                    : "r"(ta));
+            }
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            tc_arrive(b_accempty + 8 * as);                // the accumulator stage is free: the MMAs of tile it + 2 may start
+            const int Y = Y0 + r, X = X0 + c;
+            if (TILED) {
+                // the 16 x 8 tile is two 8 x 8 blocks of the tile-major layout; a warp writes 32 consecutive floats per tap.
+                // Pad pixels of an existing block (ragged H / W) are written as zeros.
+                if ((Y >> 3) < tiles_y8) {
+                    const bool ok = Y < sh.H && X < sh.W;
+                    float* p = out + (((int64_t)b * tiles_y8 + (Y >> 3)) * tiles_x8 + (X0 >> 3)) * ((int64_t)sh.cout * 64) + (Y & 7) * 8 + c;
+#pragma unroll
+                    for (int n = 0; n < TC_N; ++n)
+                        if (n < sh.cout) p[n * 64] = ok ? __uint_as_float(v[n]) + sbias[n] : 0.f;
+                }
+            } else if (Y < sh.H && X < sh.W) {
+                float* p = out + (int64_t)b * sh.cout * plane + (int64_t)Y * sh.W + X;
+#pragma unroll
+                for (int n = 0; n < TC_N; ++n)
+                    if (n < sh.cout) p[(int64_t)n * plane] = __uint_as_float(v[n]) + sbias[n];
+            }
+        }
+    } else if (warp == TC_EPI_WARPS) {
+        // ===================== MMA issuer: one lane
+        if (lane == 0) {
+            // weights: resident for the life of the CTA
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b_w), "r"(TC_W_BYTES) : "memory");
+            for (int t = 0; t < 9; ++t)
+                tc_bulk_load(base + t * TC_W_TAP_BYTES, reinterpret_cast<const char*>(wpacked) + (size_t)t * TC_W_TAP_BYTES, TC_W_TAP_BYTES, b_w);
+            tc_wait(b_w, 0);
+            // instruction descriptor: D = f32, A = B = tf32, both K-major, N = 64, M = 128
+            constexpr unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(TC_N >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < sh.ntiles; tile += gridDim.x, ++it) {
+                const int s = it & 1;
+                const unsigned ph = (it >> 1) & 1;
+                tc_wait(b_accempty + 8 * s, ph ^ 1);       // accumulator stage drained by the epilogue (passes at once the first time)
+                tc_wait(b_afull + 8 * s, ph);              // patch written and fenced by the producers
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const unsigned a_base = base + TC_OFF_A + s * TC_A_BYTES;
+                const unsigned d_tmem = tmem + s * TC_N;
+                unsigned acc = 0;
+#pragma unroll 1
+                for (int tap = 0; tap < 9; ++tap) {
+                    const unsigned a_tap = a_base + ((tap / 3) * TC_PW + (tap % 3)) * 16;
+                    const unsigned w_tap = base + tap * TC_W_TAP_BYTES;
+                    for (int ks = 0; ks < sh.k_steps; ++ks) {
+                        const uint64_t da = tc_desc(a_tap + ks * 2 * TC_NPIX * 16, TC_NPIX * 16, TC_PW * 16);
+                        const uint64_t db = tc_desc(w_tap + ks * 2 * TC_N * 16, TC_N * 16, 128);
+                        asm volatile(
+                            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                            ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+                        acc = 1;
+                    }
+                }
+                tc_commit(b_aempty + 8 * s);               // patch stage may be overwritten
+                tc_commit(b_accfull + 8 * s);              // accumulator complete
+            }
+        }
+    } else {
+        // ===================== producers: patch pixel p = ptid (180 of the 192 threads), all channel chunks
+        const int ptid = tid - (TC_EPI_WARPS + 1) * 32;
+        const int py = ptid / TC_PW, px = ptid % TC_PW;
+        const bool has_pixel = ptid < TC_NPIX;
+        const int nchunks = (sh.cin + 3) >> 2;
+        const int64_t src_plane = (int64_t)sh.h * sh.w;
+        const unsigned win = base + TC_OFF_WIN;
+        float* win_gen = reinterpret_cast<float*>(gen + TC_OFF_WIN);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < sh.ntiles; tile += gridDim.x, ++it) {
+            const int s = it & 1;
+            const unsigned ph = (it >> 1) & 1;
+            int b, Y0, X0;
+            decode(tile, b, Y0, X0);
+            const int Y = Y0 - 1 + py, X = X0 - 1 + px;
+            const bool inside = has_pixel && Y >= 0 && Y < sh.H && X >= 0 && X < sh.W;   // outside: the convolution's zero padding
+            const float* xb = x + (int64_t)b * sh.cin * src_plane;
+            const unsigned a_dst = base + TC_OFF_A + s * TC_A_BYTES + ptid * 16;
+            if (UPS) {
+                // PyTorch upsample_bilinear2d, align_corners = True: source index = scale * dst (float), cut to int;
+                // the neighbour is + 1 unless at the last row / column; weights from the fraction
+                const int sy0 = (int)(sh.ry * (float)max(Y0 - 1, 0)), sx0 = (int)(sh.rx * (float)max(X0 - 1, 0));
+                asm volatile("bar.sync 2, %0;" ::"n"(TC_PROD_THREADS) : "memory");   // everyone is done reading the previous window
+                for (int i = ptid; i < sh.cin * TC_WIN_PIX; i += TC_PROD_THREADS) {
+                    const int ch = i / TC_WIN_PIX, p = i - ch * TC_WIN_PIX;
+                    const int wy = p / TC_WIN_W, wx = p - wy * TC_WIN_W;
+                    const int gy = min(sy0 + wy, sh.h - 1), gx = min(sx0 + wx, sh.w - 1);
+                    win_gen[((ch >> 2) * TC_WIN_PIX + p) * 4 + (ch & 3)] = __ldg(xb + (int64_t)ch * src_plane + (int64_t)gy * sh.w + gx);
+                }
+                asm volatile("bar.sync 2, %0;" ::"n"(TC_PROD_THREADS) : "memory");
+                tc_wait(b_aempty + 8 * s, ph ^ 1);         // the MMAs that read this patch stage two tiles ago are complete
+                if (has_pixel) {
+                    if (inside) {
+                        const float h1r = sh.ry * (float)Y, w1r = sh.rx * (float)X;
+                        const int h1 = (int)h1r, w1 = (int)w1r;
+                        const int h1p = h1 < sh.h - 1 ? 1 : 0, w1p = w1 < sh.w - 1 ? 1 : 0;
+                        const float h1l = h1r - (float)h1, h0l = 1.f - h1l, w1l = w1r - (float)w1, w0l = 1.f - w1l;
+                        const int i00 = min(h1 - sy0, TC_WIN_H - 2) * TC_WIN_W + min(w1 - sx0, TC_WIN_W - 2);
+                        const unsigned a00 = win + i00 * 16, a01 = a00 + w1p * 16, a10 = a00 + h1p * TC_WIN_W * 16, a11 = a10 + w1p * 16;
+                        for (int ck = 0; ck < nchunks; ++ck) {
+                            const unsigned o = ck * TC_WIN_PIX * 16;
+                            const float4 v00 = lds128(a00 + o), v01 = lds128(a01 + o), v10 = lds128(a10 + o), v11 = lds128(a11 + o);
+                            sts128(a_dst + ck * TC_NPIX * 16,
+                                   to_tf32(h0l * (w0l * v00.x + w1l * v01.x) + h1l * (w0l * v10.x + w1l * v11.x)),
+                                   to_tf32(h0l * (w0l * v00.y + w1l * v01.y) + h1l * (w0l * v10.y + w1l * v11.y)),
+                                   to_tf32(h0l * (w0l * v00.z + w1l * v01.z) + h1l * (w0l * v10.z + w1l * v11.z)),
+                                   to_tf32(h0l * (w0l * v00.w + w1l * v01.w) + h1l * (w0l * v10.w + w1l * v11.w)));
+                        }
+                    } else {
+                        for (int ck = 0; ck < nchunks; ++ck) sts128(a_dst + ck * TC_NPIX * 16, 0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+            } else {
+                tc_wait(b_aempty + 8 * s, ph ^ 1);
+                if (has_pixel) {
+                    const float* xp = xb + (int64_t)min(max(Y, 0), sh.H - 1) * sh.W + min(max(X, 0), sh.W - 1);
+                    for (int ck = 0; ck < nchunks; ++ck) {
+                        float q[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int ch = ck * 4 + j;
+                            q[j] = (inside && ch < sh.cin) ? to_tf32(__ldg(xp + (int64_t)ch * src_plane)) : 0.f;
+                        }
+                        sts128(a_dst + ck * TC_NPIX * 16, q[0], q[1], q[2], q[3]);
+                    }
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core's reads
+            tc_arrive(b_afull + 8 * s);
+        }
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TC_TMEM_COLS));
+}
+
+// weights [cout][cin][3][3] -> [tap][chunk][n = 64][4], zero padded, rounded to TF32
+__global__ void tap_conv3x3_pack_kernel(const float* __restrict__ w, float* __restrict__ packed, int cin, int cout) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 9 * TC_CHUNKS * TC_N * 4) return;
+    const int j = i & 3, n = (i >> 2) % TC_N, ck = (i >> 2) / TC_N % TC_CHUNKS, tap = (i >> 2) / TC_N / TC_CHUNKS;
+    const int ch = ck * 4 + j;
+    packed[i] = (n < cout && ch < cin) ? to_tf32(w[((int64_t)n * cin + ch) * 9 + tap]) : 0.f;
+}
+
+template <bool UPS, bool TILED>
+int launch_tap_conv(const float* x, const float* wpacked, const float* bias, float* out, const TapConvShape& sh, cudaStream_t s) {
+    static PerDeviceOnce done;
+    auto kern = tap_conv3x3_kernel<UPS, TILED>;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!done.test(dev)) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM) != cudaSuccess) return (int)cudaGetLastError();
+        done.set(dev);
+    }
+    const int ctas = std::min(sh.ntiles, sm_count());
+    kern<<<ctas, TC_THREADS, TC_SMEM, s>>>(x, wpacked, bias, out, sh);
+    count_launch();
+    return finish_launch();
+}
+
+}  // namespace
+
+}  // namespace sstem
+
+using namespace sstem;
+
+extern "C" int64_t sstem_tap_conv3x3_packed_elems(void) { return (int64_t)TC_W_BYTES / 4; }
+
+extern "C" int sstem_tap_conv3x3_pack_weights(const float* weight, float* packed, int32_t cin, int32_t cout, void* stream) {
+    if (!weight || !packed) return SSTEM_E_NULL;
+    if (cin <= 0 || cin > TC_MAXC || cout <= 0 || cout > TC_N) return SSTEM_E_SHAPE;
+    if (!aligned4(weight) || !aligned16(packed)) return SSTEM_E_ALIGN;
+    DeviceGuard guard(packed);
+    if (guard.err) return guard.err;
+    const int total = 9 * TC_CHUNKS * TC_N * 4;
+    tap_conv3x3_pack_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(weight, packed, cin, cout);
+    count_launch();
+    return finish_launch();
+}
+
+extern "C" int sstem_tap_conv3x3(const float* x, const float* packed_weight, const float* bias, float* out,
+                                 int64_t B, int32_t cin, int32_t cout, int64_t h, int64_t w, uint32_t flags, void* stream) {
+    if (!x || !packed_weight || !out) return SSTEM_E_NULL;
+    if (flags & ~(SSTEM_TAPCONV_UPSAMPLE2X | SSTEM_TAPCONV_TILED)) return SSTEM_E_FLAG;
+    const bool ups = flags & SSTEM_TAPCONV_UPSAMPLE2X, tiled = flags & SSTEM_TAPCONV_TILED;
+    if (B <= 0 || h <= 0 || w <= 0 || h > (1 << 22) || w > (1 << 22)) return SSTEM_E_SHAPE;
+    if (cin <= 0 || cin > TC_MAXC || cout <= 0 || cout > TC_N) return SSTEM_E_SHAPE;
+    if (tiled && cout != 51) return SSTEM_E_SHAPE;         // the tile-major layout is the 51-tap consumer's
+    if (!aligned4(x) || !aligned16(packed_weight) || !aligned4(out) || (bias && !aligned4(bias))) return SSTEM_E_ALIGN;
+    DeviceGuard guard(out);
+    if (guard.err) return guard.err;
+    TapConvShape sh;
+    sh.B = (int)B; sh.cin = cin; sh.cout = cout; sh.h = (int)h; sh.w = (int)w;
+    sh.H = ups ? 2 * (int)h : (int)h;
+    sh.W = ups ? 2 * (int)w : (int)w;
+    sh.tiles_x = (sh.W + TC_TW - 1) / TC_TW;
+    sh.tiles_y = (sh.H + TC_TH - 1) / TC_TH;
+    const int64_t nt = (int64_t)sh.tiles_x * sh.tiles_y * B;
+    if (nt > INT32_MAX / 2) return SSTEM_E_SHAPE;
+    sh.ntiles = (int)nt;
+    sh.k_steps = (cin + 7) / 8;
+    sh.ry = sh.H > 1 ? (float)(sh.h - 1) / (float)(sh.H - 1) : 0.f;
+    sh.rx = sh.W > 1 ? (float)(sh.w - 1) / (float)(sh.W - 1) : 0.f;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (ups) return tiled ? launch_tap_conv<true, true>(x, packed_weight, bias, out, sh, s) : launch_tap_conv<true, false>(x, packed_weight, bias, out, sh, s);
+    return tiled ? launch_tap_conv<false, true>(x, packed_weight, bias, out, sh, s) : launch_tap_conv<false, false>(x, packed_weight, bias, out, sh, s);
+}

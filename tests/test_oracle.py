@@ -257,3 +257,18 @@ def test_warp_backward_restatement_matches_reference_autograd(golden_dir):
         gm, gf = oracle.warp_torch_backward_restated(mv, fl, upstream(name, mv.shape))
         assert np.abs(gm - ref[name + "_gm"]).max() <= 2e-5 * max(1.0, np.abs(ref[name + "_gm"]).max()), name
         assert np.abs(gf - ref[name + "_gf"]).max() <= 2e-5 * max(1.0, np.abs(ref[name + "_gf"]).max()), name
+
+
+def test_tap_producer_restatement_matches_reference_model(golden_dir):
+    """upsample(align_corners=True) -> Conv2d(51,51,3,1,1) of the reference's own IFNet tap branch, run on CPU
+    (tests/golden/make_tap_producer_golden.py): indices / weights as ATen, so fp32 agrees to rounding."""
+    g = np.load(os.path.join(golden_dir, "tap_producer_ref.npz"))
+    up32 = oracle.upsample2x_align_corners_restated(g["x"], np.float32)
+    assert np.abs(up32[:, :4] - g["up_c0_3"]).max() <= 5e-7
+    y = oracle.tap_conv3x3_restated(g["x"], g["weight"], g["bias"])
+    assert y.shape == g["y"].shape and np.abs(y - g["y"]).max() <= 5e-6
+    # without the upsample it is a plain zero-padded cross-correlation
+    r = np.random.default_rng(0)
+    x, w = r.standard_normal((1, 3, 5, 6)), r.standard_normal((2, 3, 3, 3))
+    want = torch.nn.functional.conv2d(torch.from_numpy(x), torch.from_numpy(w), padding=1).numpy()
+    assert np.abs(oracle.tap_conv3x3_restated(x, w, None, upsample=False) - want).max() <= 1e-12
