@@ -296,9 +296,9 @@ int sstem_sepconv_forward_tiled(const float* input, const float* vertical_tiled,
  * folded into the operand producer, the result written [B,cout,H,W] or directly tile-major (SSTEM_TAPCONV_TILED, the
  * layout of sstem_sepconv_forward_tiled; cout must then be 51).
  *
- *   x       [B, cin, h, w]      cin <= 56
+ *   x       [B, cin, h, w]      cin <= 52
  *   weight  [cout, cin, 3, 3]   cout <= 64 (torch's Conv2d.weight); packed once by sstem_tap_conv3x3_pack_weights into
- *                               sstem_tap_conv3x3_packed_elems() floats ([tap][cin chunk of 4][64][4], rounded to TF32)
+ *                               sstem_tap_conv3x3_packed_elems() floats ([tap][cin chunk of 4 < 13][64][4] + a zero chunk, rounded to TF32)
  *   bias    [cout] or NULL
  *   out     [B, cout, H, W] or tiled; (H, W) = (2h, 2w) with SSTEM_TAPCONV_UPSAMPLE2X, else (h, w)
  *

@@ -20,6 +20,8 @@
 //     warps (source window -> shared memory, bilinear blend with PyTorch's own index / weight expressions, round to
 //     TF32, write the patch); mbarriers between them, a persistent grid of one CTA per SM.
 // Shared memory bandwidth bounds the kernel (each MMA reads 4 KB of A and 2 KB of W for 65 536 FMAs); see DESIGN 4.11.
+#include <string.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -28,24 +30,34 @@
 namespace sstem {
 namespace {
 
-constexpr int TC_MAXC = 56;                                // input channels, padded to chunks of 4 and K-steps of 8
-constexpr int TC_CHUNKS = TC_MAXC / 4;                     // 14
+constexpr int TC_MAXC = 52;                                // input channels: 13 chunks of 4
+constexpr int TC_WCHUNKS = TC_MAXC / 4;                    // 13 weight chunks per tap (+ one zero chunk shared by all taps)
+constexpr int TC_CHUNKS = TC_WCHUNKS + 1;                  // 14 patch chunks = 7 K-steps of 8; chunk 13 is always zero
 constexpr int TC_N = 64;                                   // output channels, padded (UMMA N)
 constexpr int TC_TH = 16, TC_TW = 8;                       // output tile: 128 pixels = UMMA M
 constexpr int TC_PH = TC_TH + 2, TC_PW = TC_TW + 2, TC_NPIX = TC_PH * TC_PW;   // 18 x 10 = 180
-constexpr int TC_WIN_H = 11, TC_WIN_W = 7, TC_WIN_PIX = TC_WIN_H * TC_WIN_W;   // half-resolution source window
-constexpr unsigned TC_W_TAP_BYTES = TC_CHUNKS * TC_N * 16;                     // 14336
-constexpr unsigned TC_W_BYTES = 9 * TC_W_TAP_BYTES;                            // 129024
+// Half-resolution source window: 11 rows x up to 7 columns are used; a TMA box must start on a 16-byte boundary in
+// global memory, so the first column is rounded down to a multiple of 4 and 12 columns are loaded (48-byte rows).
+constexpr int TC_WIN_H = 11, TC_WIN_W = 12;
+constexpr int TC_WIN_CH = TC_WIN_H * TC_WIN_W;             // 132 floats = 528 bytes per channel: [channel][row][column]
+constexpr int TC_WIN_GROUPS = 2, TC_WIN_GROUP_CH = 28;     // two channel groups (chunks 0-6, 7-12), loaded and consumed in turn
+constexpr unsigned TC_WIN_GROUP_BYTES = TC_WIN_GROUP_CH * TC_WIN_CH * 4;       // 14784: what one TMA box delivers
+constexpr unsigned TC_WIN_GROUP_PITCH = (TC_WIN_GROUP_BYTES + 127) / 128 * 128;   // 14848
+constexpr unsigned TC_W_TAP_BYTES = TC_WCHUNKS * TC_N * 16;                    // 13312
+constexpr unsigned TC_W_ZERO_OFF = 9 * TC_W_TAP_BYTES;                         // 119808: the zero chunk
+constexpr unsigned TC_W_BYTES = TC_W_ZERO_OFF + TC_N * 16;                     // 120832
 constexpr unsigned TC_A_BYTES = TC_CHUNKS * TC_NPIX * 16;                      // 40320
-constexpr unsigned TC_WIN_BYTES = (TC_CHUNKS * TC_WIN_PIX * 16 + 127) / 128 * 128;         // 17280
+constexpr unsigned TC_WIN_BYTES = TC_WIN_GROUPS * TC_WIN_GROUP_PITCH;          // 29696
 constexpr unsigned TC_OFF_A = TC_W_BYTES;
 constexpr unsigned TC_OFF_WIN = TC_OFF_A + 2 * TC_A_BYTES;
 constexpr unsigned TC_OFF_BIAS = TC_OFF_WIN + TC_WIN_BYTES;
 constexpr unsigned TC_OFF_BAR = TC_OFF_BIAS + TC_N * 4;
-constexpr unsigned TC_SMEM = TC_OFF_BAR + 128 + 128;       // + barriers + alignment slack = 227 456 (of 232 448)
-constexpr int TC_EPI_WARPS = 4, TC_PROD_WARPS = 6;
-constexpr int TC_THREADS = (TC_EPI_WARPS + 1 + TC_PROD_WARPS) * 32;            // 352
-constexpr int TC_PROD_THREADS = TC_PROD_WARPS * 32;                            // 192 >= 180 patch pixels
+constexpr unsigned TC_SMEM = TC_OFF_BAR + 128 + 128;       // + barriers + alignment slack = 231 680 (of 232 448)
+static_assert(TC_SMEM <= 232448, "shared memory budget");
+constexpr int TC_EPI_WARPS = 4, TC_PROD_WARPS = 12;
+constexpr int TC_THREADS = (TC_EPI_WARPS + 1 + TC_PROD_WARPS) * 32;            // 544
+constexpr int TC_PROD_THREADS = TC_PROD_WARPS * 32;                            // 384 = 2 x 192: (patch pixel, chunk parity)
+constexpr int TC_PIX_THREADS = TC_PROD_THREADS / 2;                            // 192 >= 180 patch pixels
 constexpr unsigned TC_TMEM_COLS = 128;                     // two accumulator stages of 64 columns
 
 struct TapConvShape {
@@ -92,23 +104,26 @@ __device__ __forceinline__ float to_tf32(float x) {        // round to nearest (
 __device__ __forceinline__ void sts128(unsigned addr, float a, float b, float c, float d) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
-__device__ __forceinline__ float4 lds128(unsigned addr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+__device__ __forceinline__ float lds_f32(unsigned addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
     return v;
 }
 
-template <bool UPS, bool TILED>
+// UPS: fold the x2 upsample into the producer.  WTMA (UPS only): the source window arrives by TMA (needs w % 4 == 0 and a
+// 16-byte aligned x); otherwise the producers gather it with plain loads.
+// FULL (WTMA only): cin is 49..52, i.e. all 13 chunks exist -- the blend loop then has no per-chunk checks.
+template <bool UPS, bool TILED, bool WTMA, bool FULL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-tap_conv3x3_kernel(const float* __restrict__ x, const float* __restrict__ wpacked, const float* __restrict__ bias,
-                   float* __restrict__ out, const TapConvShape sh) {
+tap_conv3x3_kernel(const __grid_constant__ CUtensorMap map_x, const float* __restrict__ x, const float* __restrict__ wpacked,
+                   const float* __restrict__ bias, float* __restrict__ out, const TapConvShape sh) {
     extern __shared__ __align__(128) unsigned char tc_smem_raw[];
     const unsigned base = ((unsigned)__cvta_generic_to_shared(tc_smem_raw) + 127u) & ~127u;
     unsigned char* gen = tc_smem_raw + (base - (unsigned)__cvta_generic_to_shared(tc_smem_raw));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // barriers: 0 weights, 1-2 a_full, 3-4 a_empty, 5-6 acc_full, 7-8 acc_empty; the TMEM base address after them
+    // barriers: 0 weights, 1-2 a_full, 3-4 a_empty, 5-6 acc_full, 7-8 acc_empty, 9-10 win_full; the TMEM base address after them
     const unsigned bar = base + TC_OFF_BAR;
-    const unsigned b_w = bar, b_afull = bar + 8, b_aempty = bar + 24, b_accfull = bar + 40, b_accempty = bar + 56;
+    const unsigned b_w = bar, b_afull = bar + 8, b_aempty = bar + 24, b_accfull = bar + 40, b_accempty = bar + 56, b_winfull = bar + 72;
     volatile unsigned* tmem_slot = reinterpret_cast<volatile unsigned*>(gen + TC_OFF_BAR + 96);
 
     if (tid == 0) {
@@ -118,13 +133,13 @@ tap_conv3x3_kernel(const float* __restrict__ x, const float* __restrict__ wpacke
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b_aempty + 8 * s));
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b_accfull + 8 * s));
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b_accempty + 8 * s), "r"(TC_EPI_WARPS * 32));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b_winfull + 8 * s));
         }
         mbar_fence_init();
     }
     // zero both patches once (the chunks past cin and the pad pixels a tile never writes must be finite) and the bias pad
     for (unsigned i = tid; i < 2 * TC_A_BYTES / 16; i += TC_THREADS) sts128(base + TC_OFF_A + i * 16, 0.f, 0.f, 0.f, 0.f);
-    for (unsigned i = tid; i < TC_WIN_BYTES / 16; i += TC_THREADS) sts128(base + TC_OFF_WIN + i * 16, 0.f, 0.f, 0.f, 0.f);
-    if (tid < TC_N) reinterpret_cast<float*>(gen + TC_OFF_BIAS)[tid] = (bias != nullptr && tid < sh.cout) ? bias[tid] : 0.f;
+        if (tid < TC_N) reinterpret_cast<float*>(gen + TC_OFF_BIAS)[tid] = (bias != nullptr && tid < sh.cout) ? bias[tid] : 0.f;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (warp == 0) {
         __syncwarp();
@@ -136,11 +151,28 @@ tap_conv3x3_kernel(const float* __restrict__ x, const float* __restrict__ wpacke
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const unsigned tmem = *tmem_slot;
 
-    auto decode = [&](int t, int& b, int& Y0, int& X0) {
-        const int tx = t % sh.tiles_x, r = t / sh.tiles_x;
-        X0 = tx * TC_TW;
-        Y0 = (r % sh.tiles_y) * TC_TH;
-        b = r / sh.tiles_y;
+    // A CTA walks tiles blockIdx.x, + gridDim.x, ...; the tile coordinates advance by a fixed (column, row) step, so
+    // the loop needs no division (two 32-bit divisions per tile and warp were 15 % of all instructions issued).
+    struct TileIter {
+        int tile, tx, ty, b;
+    };
+    const int step_tx = (int)gridDim.x % sh.tiles_x, step_r = (int)gridDim.x / sh.tiles_x;
+    auto first_tile = [&]() {
+        TileIter t;
+        t.tile = blockIdx.x;
+        const int r = t.tile / sh.tiles_x;
+        t.tx = t.tile - r * sh.tiles_x;
+        t.b = r / sh.tiles_y;
+        t.ty = r - t.b * sh.tiles_y;
+        return t;
+    };
+    auto advance = [&](TileIter& t) {
+        t.tile += gridDim.x;
+        t.tx += step_tx;
+        int dr = step_r;
+        if (t.tx >= sh.tiles_x) { t.tx -= sh.tiles_x; ++dr; }
+        t.ty += dr;
+        while (t.ty >= sh.tiles_y) { t.ty -= sh.tiles_y; ++t.b; }
     };
 
     if (warp < TC_EPI_WARPS) {
@@ -150,10 +182,9 @@ tap_conv3x3_kernel(const float* __restrict__ x, const float* __restrict__ wpacke
         const int64_t plane = (int64_t)sh.H * sh.W;
         const int tiles_y8 = (sh.H + 7) / 8, tiles_x8 = (sh.W + 7) / 8;
         int it = 0;
-        for (int tile = blockIdx.x; tile < sh.ntiles; tile += gridDim.x, ++it) {
+        for (TileIter ti = first_tile(); ti.tile < sh.ntiles; advance(ti), ++it) {
             const int as = it & 1;
-            int b, Y0, X0;
-            decode(tile, b, Y0, X0);
+            const int b = ti.b, Y0 = ti.ty * TC_TH, X0 = ti.tx * TC_TW;
             tc_wait(b_accfull + 8 * as, (it >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             unsigned v[64];
@@ -176,14 +207,24 @@ tap_conv3x3_kernel(const float* __restrict__ x, const float* __restrict__ wpacke
             tc_arrive(b_accempty + 8 * as);                // the accumulator stage is free: the MMAs of tile it + 2 may start
             const int Y = Y0 + r, X = X0 + c;
             if (TILED) {
-                // the 16 x 8 tile is two 8 x 8 blocks of the tile-major layout; a warp writes 32 consecutive floats per tap.
-                // Pad pixels of an existing block (ragged H / W) are written as zeros.
+                // the 16 x 8 tile is two 8 x 8 blocks of the tile-major layout; a warp writes 32 consecutive floats per tap
+                // (cout == 51 here).  Pad pixels of an existing block (ragged H / W) are written as zeros.
                 if ((Y >> 3) < tiles_y8) {
-                    const bool ok = Y < sh.H && X < sh.W;
-                    float* p = out + (((int64_t)b * tiles_y8 + (Y >> 3)) * tiles_x8 + (X0 >> 3)) * ((int64_t)sh.cout * 64) + (Y & 7) * 8 + c;
+                    float* p = out + (((int64_t)b * tiles_y8 + (Y >> 3)) * tiles_x8 + (X0 >> 3)) * (51 * 64) + (Y & 7) * 8 + c;
+                    if (Y0 + TC_TH <= sh.H && X0 + TC_TW <= sh.W) {   // the whole tile is inside the image: no masks
 #pragma unroll
-                    for (int n = 0; n < TC_N; ++n)
-                        if (n < sh.cout) p[n * 64] = ok ? __uint_as_float(v[n]) + sbias[n] : 0.f;
+                        for (int n4 = 0; n4 < 52; n4 += 4) {
+                            const float4 b4 = *reinterpret_cast<const float4*>(sbias + n4);
+                            p[(n4 + 0) * 64] = __uint_as_float(v[n4 + 0]) + b4.x;
+                            p[(n4 + 1) * 64] = __uint_as_float(v[n4 + 1]) + b4.y;
+                            p[(n4 + 2) * 64] = __uint_as_float(v[n4 + 2]) + b4.z;
+                            if (n4 + 3 < 51) p[(n4 + 3) * 64] = __uint_as_float(v[n4 + 3]) + b4.w;
+                        }
+                    } else {
+                        const bool ok = Y < sh.H && X < sh.W;
+#pragma unroll
+                        for (int n = 0; n < 51; ++n) p[n * 64] = ok ? __uint_as_float(v[n]) + sbias[n] : 0.f;
+                    }
                 }
             } else if (Y < sh.H && X < sh.W) {
                 float* p = out + (int64_t)b * sh.cout * plane + (int64_t)Y * sh.W + X;
@@ -199,11 +240,12 @@ tap_conv3x3_kernel(const float* __restrict__ x, const float* __restrict__ wpacke
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b_w), "r"(TC_W_BYTES) : "memory");
             for (int t = 0; t < 9; ++t)
                 tc_bulk_load(base + t * TC_W_TAP_BYTES, reinterpret_cast<const char*>(wpacked) + (size_t)t * TC_W_TAP_BYTES, TC_W_TAP_BYTES, b_w);
+            tc_bulk_load(base + TC_W_ZERO_OFF, reinterpret_cast<const char*>(wpacked) + TC_W_ZERO_OFF, TC_N * 16, b_w);
             tc_wait(b_w, 0);
             // instruction descriptor: D = f32, A = B = tf32, both K-major, N = 64, M = 128
             constexpr unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(TC_N >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
             int it = 0;
-            for (int tile = blockIdx.x; tile < sh.ntiles; tile += gridDim.x, ++it) {
+            for (int tile = blockIdx.x; tile < sh.ntiles; tile += gridDim.x, ++it) {   // (needs no coordinates)
                 const int s = it & 1;
                 const unsigned ph = (it >> 1) & 1;
                 tc_wait(b_accempty + 8 * s, ph ^ 1);       // accumulator stage drained by the epilogue (passes at once the first time)
@@ -218,7 +260,10 @@ tap_conv3x3_kernel(const float* __restrict__ x, const float* __restrict__ wpacke
                     const unsigned w_tap = base + tap * TC_W_TAP_BYTES;
                     for (int ks = 0; ks < sh.k_steps; ++ks) {
                         const uint64_t da = tc_desc(a_tap + ks * 2 * TC_NPIX * 16, TC_NPIX * 16, TC_PW * 16);
-                        const uint64_t db = tc_desc(w_tap + ks * 2 * TC_N * 16, TC_N * 16, 128);
+                        // the K-step's second weight chunk; past chunk 12 it is the zero chunk all taps share (the patch's chunk 13 is zero too)
+                        const unsigned w_lo = w_tap + ks * 2 * TC_N * 16;
+                        const unsigned w_lbo = (2 * ks + 1 < TC_WCHUNKS) ? TC_N * 16 : base + TC_W_ZERO_OFF - w_lo;
+                        const uint64_t db = tc_desc(w_lo, w_lbo, 128);
                         asm volatile(
                             "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                             "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
@@ -231,70 +276,141 @@ tap_conv3x3_kernel(const float* __restrict__ x, const float* __restrict__ wpacke
             }
         }
     } else {
-        // ===================== producers: patch pixel p = ptid (180 of the 192 threads), all channel chunks
+        // ===================== producers: thread = (patch pixel, chunk parity); 180 of each 192 threads have a pixel
         const int ptid = tid - (TC_EPI_WARPS + 1) * 32;
-        const int py = ptid / TC_PW, px = ptid % TC_PW;
-        const bool has_pixel = ptid < TC_NPIX;
+        const int half = ptid >= TC_PIX_THREADS ? 1 : 0, pix = ptid - half * TC_PIX_THREADS;
+        const int py = pix / TC_PW, px = pix % TC_PW;
+        const bool has_pixel = pix < TC_NPIX;
         const int nchunks = (sh.cin + 3) >> 2;
         const int64_t src_plane = (int64_t)sh.h * sh.w;
         const unsigned win = base + TC_OFF_WIN;
         float* win_gen = reinterpret_cast<float*>(gen + TC_OFF_WIN);
+        auto window_origin = [&](int Y0, int X0, int& sy0, int& sx0) {
+            // PyTorch upsample_bilinear2d, align_corners = True: source index = scale * dst in float, cut to int
+            sy0 = (int)(sh.ry * (float)max(Y0 - 1, 0));
+            sx0 = (int)(sh.rx * (float)max(X0 - 1, 0)) & ~3;       // 16-byte aligned box start
+        };
+        // WTMA: one elected thread asks the TMA unit for the two channel groups of a tile's window
+        auto issue_window = [&](const TileIter& t, int g) {
+            int sy0, sx0;
+            const int b = t.b;
+            window_origin(t.ty * TC_TH, t.tx * TC_TW, sy0, sx0);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b_winfull + 8 * g), "r"(TC_WIN_GROUP_BYTES) : "memory");
+            asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                         ::"r"(win + g * TC_WIN_GROUP_PITCH), "l"(reinterpret_cast<uint64_t>(&map_x)), "r"(b_winfull + 8 * g),
+                           "r"(sx0), "r"(sy0), "r"(g * TC_WIN_GROUP_CH), "r"(b) : "memory");
+        };
+        // !WTMA: the window of tile i + 1 is gathered into registers while tile i's patch is computed
+        constexpr int NFILL = WTMA ? 1 : (TC_MAXC * TC_WIN_CH + TC_PROD_THREADS - 1) / TC_PROD_THREADS;   // 18
+        float pre[NFILL];
+        auto load_window = [&](const TileIter& t) {
+            int sy0, sx0;
+            const int b = t.b;
+            window_origin(t.ty * TC_TH, t.tx * TC_TW, sy0, sx0);
+            const float* xb = x + (int64_t)b * sh.cin * src_plane;
+#pragma unroll
+            for (int k = 0; k < NFILL; ++k) {
+                const int i = ptid + k * TC_PROD_THREADS;
+                const int ch = i / TC_WIN_CH, p = i - ch * TC_WIN_CH;
+                const int wy = p / TC_WIN_W, wx = p - wy * TC_WIN_W;
+                const int gy = min(sy0 + wy, sh.h - 1), gx = min(sx0 + wx, sh.w - 1);
+                pre[k] = ch < sh.cin ? __ldg(xb + (int64_t)ch * src_plane + (int64_t)gy * sh.w + gx) : 0.f;
+            }
+        };
+        auto store_window = [&]() {
+#pragma unroll
+            for (int k = 0; k < NFILL; ++k) {
+                const int i = ptid + k * TC_PROD_THREADS;
+                const int ch = i / TC_WIN_CH, p = i - ch * TC_WIN_CH;
+                const int g = ch >= TC_WIN_GROUP_CH ? 1 : 0;
+                if (ch < TC_MAXC) win_gen[g * (TC_WIN_GROUP_PITCH / 4) + (ch - g * TC_WIN_GROUP_CH) * TC_WIN_CH + p] = pre[k];
+            }
+        };
+        TileIter ti = first_tile(), tn = ti;               // this tile and the next one of this CTA
+        advance(tn);
+        if (UPS && ti.tile < sh.ntiles) {
+            if (WTMA) { if (ptid == 0) { issue_window(ti, 0); issue_window(ti, 1); } }
+            else load_window(ti);
+        }
+        // per-thread constants of the blend: chunk parity folded into the base addresses, so every shared-memory offset
+        // below is an immediate
+        const unsigned half_win = half * 4 * (TC_WIN_CH * 4), half_dst = half * TC_NPIX * 16;
         int it = 0;
-        for (int tile = blockIdx.x; tile < sh.ntiles; tile += gridDim.x, ++it) {
+        for (; ti.tile < sh.ntiles; ti = tn, advance(tn), ++it) {
             const int s = it & 1;
             const unsigned ph = (it >> 1) & 1;
-            int b, Y0, X0;
-            decode(tile, b, Y0, X0);
+            const int b = ti.b, Y0 = ti.ty * TC_TH, X0 = ti.tx * TC_TW;
             const int Y = Y0 - 1 + py, X = X0 - 1 + px;
             const bool inside = has_pixel && Y >= 0 && Y < sh.H && X >= 0 && X < sh.W;   // outside: the convolution's zero padding
-            const float* xb = x + (int64_t)b * sh.cin * src_plane;
-            const unsigned a_dst = base + TC_OFF_A + s * TC_A_BYTES + ptid * 16;
+            const unsigned a_dst = base + TC_OFF_A + s * TC_A_BYTES + pix * 16 + half_dst;
+            const bool has_next = tn.tile < sh.ntiles;
             if (UPS) {
-                // PyTorch upsample_bilinear2d, align_corners = True: source index = scale * dst (float), cut to int;
-                // the neighbour is + 1 unless at the last row / column; weights from the fraction
-                const int sy0 = (int)(sh.ry * (float)max(Y0 - 1, 0)), sx0 = (int)(sh.rx * (float)max(X0 - 1, 0));
-                asm volatile("bar.sync 2, %0;" ::"n"(TC_PROD_THREADS) : "memory");   // everyone is done reading the previous window
-                for (int i = ptid; i < sh.cin * TC_WIN_PIX; i += TC_PROD_THREADS) {
-                    const int ch = i / TC_WIN_PIX, p = i - ch * TC_WIN_PIX;
-                    const int wy = p / TC_WIN_W, wx = p - wy * TC_WIN_W;
-                    const int gy = min(sy0 + wy, sh.h - 1), gx = min(sx0 + wx, sh.w - 1);
-                    win_gen[((ch >> 2) * TC_WIN_PIX + p) * 4 + (ch & 3)] = __ldg(xb + (int64_t)ch * src_plane + (int64_t)gy * sh.w + gx);
+                int sy0, sx0;
+                window_origin(Y0, X0, sy0, sx0);
+                // neighbour = + 1 unless at the last row / column; weights from the fraction.  The four weights are multiplied
+                // out first (ATen nests them); the difference is an fp32 rounding, far below the TF32 rounding that follows.
+                const float h1r = sh.ry * (float)Y, w1r = sh.rx * (float)X;
+                const int h1 = (int)h1r, w1 = (int)w1r;
+                const int h1p = h1 < sh.h - 1 ? 1 : 0, w1p = w1 < sh.w - 1 ? 1 : 0;
+                const float h1l = h1r - (float)h1, h0l = 1.f - h1l, w1l = w1r - (float)w1, w0l = 1.f - w1l;
+                const float wa = h0l * w0l, wb = h0l * w1l, wc = h1l * w0l, wd = h1l * w1l;
+                const int cell = min(max(h1 - sy0, 0), TC_WIN_H - 2) * TC_WIN_W + min(max(w1 - sx0, 0), TC_WIN_W - 2);
+                const unsigned a00 = win + cell * 4 + half_win, a01 = a00 + w1p * 4, a10 = a00 + h1p * TC_WIN_W * 4, a11 = a10 + w1p * 4;
+                if (!WTMA) {
+                    asm volatile("bar.sync 2, %0;" ::"n"(TC_PROD_THREADS) : "memory");   // everyone is done reading the previous window
+                    store_window();
+                    asm volatile("bar.sync 2, %0;" ::"n"(TC_PROD_THREADS) : "memory");
+                    if (has_next) load_window(tn);
                 }
-                asm volatile("bar.sync 2, %0;" ::"n"(TC_PROD_THREADS) : "memory");
-                tc_wait(b_aempty + 8 * s, ph ^ 1);         // the MMAs that read this patch stage two tiles ago are complete
-                if (has_pixel) {
-                    if (inside) {
-                        const float h1r = sh.ry * (float)Y, w1r = sh.rx * (float)X;
-                        const int h1 = (int)h1r, w1 = (int)w1r;
-                        const int h1p = h1 < sh.h - 1 ? 1 : 0, w1p = w1 < sh.w - 1 ? 1 : 0;
-                        const float h1l = h1r - (float)h1, h0l = 1.f - h1l, w1l = w1r - (float)w1, w0l = 1.f - w1l;
-                        const int i00 = min(h1 - sy0, TC_WIN_H - 2) * TC_WIN_W + min(w1 - sx0, TC_WIN_W - 2);
-                        const unsigned a00 = win + i00 * 16, a01 = a00 + w1p * 16, a10 = a00 + h1p * TC_WIN_W * 16, a11 = a10 + w1p * 16;
-                        for (int ck = 0; ck < nchunks; ++ck) {
-                            const unsigned o = ck * TC_WIN_PIX * 16;
-                            const float4 v00 = lds128(a00 + o), v01 = lds128(a01 + o), v10 = lds128(a10 + o), v11 = lds128(a11 + o);
-                            sts128(a_dst + ck * TC_NPIX * 16,
-                                   to_tf32(h0l * (w0l * v00.x + w1l * v01.x) + h1l * (w0l * v10.x + w1l * v11.x)),
-                                   to_tf32(h0l * (w0l * v00.y + w1l * v01.y) + h1l * (w0l * v10.y + w1l * v11.y)),
-                                   to_tf32(h0l * (w0l * v00.z + w1l * v01.z) + h1l * (w0l * v10.z + w1l * v11.z)),
-                                   to_tf32(h0l * (w0l * v00.w + w1l * v01.w) + h1l * (w0l * v10.w + w1l * v11.w)));
+#pragma unroll
+                for (int g = 0; g < TC_WIN_GROUPS; ++g) {
+                    if (WTMA) tc_wait(b_winfull + 8 * g, it & 1);
+                    if (g == 0) tc_wait(b_aempty + 8 * s, ph ^ 1);     // the MMAs that read this patch stage two tiles ago are complete
+                    if (has_pixel) {
+                        // this thread's chunks of the group: 7 g + half + 2 k.  With 13 chunks (cin 49..52, FULL) that is
+                        // k < 3, plus k = 3 for the even chunks of group 0; otherwise each chunk is checked against cin.
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int ck = g * (TC_CHUNKS / 2) + half + 2 * k;
+                            const bool mine = FULL ? (k < 3 || (g == 0 && half == 0)) : (ck < (g + 1) * (TC_CHUNKS / 2) && ck < nchunks);
+                            if (!mine) continue;
+                            const unsigned dst = a_dst + (g * (TC_CHUNKS / 2) + 2 * k) * TC_NPIX * 16;
+                            if (inside) {
+                                float q[4];
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const unsigned o = g * TC_WIN_GROUP_PITCH + (unsigned)(8 * k + j) * (TC_WIN_CH * 4);
+                                    q[j] = to_tf32(wa * lds_f32(a00 + o) + wb * lds_f32(a01 + o) + wc * lds_f32(a10 + o) + wd * lds_f32(a11 + o));
+                                }
+                                sts128(dst, q[0], q[1], q[2], q[3]);
+                            } else {
+                                sts128(dst, 0.f, 0.f, 0.f, 0.f);
+                            }
                         }
-                    } else {
-                        for (int ck = 0; ck < nchunks; ++ck) sts128(a_dst + ck * TC_NPIX * 16, 0.f, 0.f, 0.f, 0.f);
+                    }
+                    if (WTMA) {
+                        asm volatile("bar.sync 2, %0;" ::"n"(TC_PROD_THREADS) : "memory");   // the group's window has been read by everyone
+                        if (ptid == 0 && has_next) issue_window(tn, g);
                     }
                 }
             } else {
+                const float* xb = x + (int64_t)b * sh.cin * src_plane;
                 tc_wait(b_aempty + 8 * s, ph ^ 1);
                 if (has_pixel) {
                     const float* xp = xb + (int64_t)min(max(Y, 0), sh.H - 1) * sh.W + min(max(X, 0), sh.W - 1);
-                    for (int ck = 0; ck < nchunks; ++ck) {
-                        float q[4];
+#pragma unroll 1
+                    for (int ck0 = half; ck0 < nchunks; ck0 += 8) {    // chunks half, half + 2, ...: 16 independent loads in flight per thread
+                        const unsigned dst0 = a_dst - half_dst;
+                        float q[16];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int ch = ck * 4 + j;
-                            q[j] = (inside && ch < sh.cin) ? to_tf32(__ldg(xp + (int64_t)ch * src_plane)) : 0.f;
+                        for (int j = 0; j < 16; ++j) {
+                            const int ch = (ck0 + 2 * (j >> 2)) * 4 + (j & 3);
+                            q[j] = (inside && ch < sh.cin) ? __ldg(xp + (int64_t)ch * src_plane) : 0.f;
                         }
-                        sts128(a_dst + ck * TC_NPIX * 16, q[0], q[1], q[2], q[3]);
+#pragma unroll
+                        for (int c4 = 0; c4 < 4; ++c4)
+                            if (ck0 + 2 * c4 < nchunks)
+                                sts128(dst0 + (ck0 + 2 * c4) * TC_NPIX * 16, to_tf32(q[4 * c4]), to_tf32(q[4 * c4 + 1]), to_tf32(q[4 * c4 + 2]), to_tf32(q[4 * c4 + 3]));
                     }
                 }
             }
@@ -308,19 +424,20 @@ tap_conv3x3_kernel(const float* __restrict__ x, const float* __restrict__ wpacke
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TC_TMEM_COLS));
 }
 
-// weights [cout][cin][3][3] -> [tap][chunk][n = 64][4], zero padded, rounded to TF32
+// weights [cout][cin][3][3] -> [tap][chunk < 13][n = 64][4] + one zero chunk, zero padded, rounded to TF32
 __global__ void tap_conv3x3_pack_kernel(const float* __restrict__ w, float* __restrict__ packed, int cin, int cout) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 9 * TC_CHUNKS * TC_N * 4) return;
-    const int j = i & 3, n = (i >> 2) % TC_N, ck = (i >> 2) / TC_N % TC_CHUNKS, tap = (i >> 2) / TC_N / TC_CHUNKS;
+    if (i >= (int)(TC_W_BYTES / 4)) return;
+    if (i >= (int)(TC_W_ZERO_OFF / 4)) { packed[i] = 0.f; return; }
+    const int j = i & 3, n = (i >> 2) % TC_N, ck = (i >> 2) / TC_N % TC_WCHUNKS, tap = (i >> 2) / TC_N / TC_WCHUNKS;
     const int ch = ck * 4 + j;
     packed[i] = (n < cout && ch < cin) ? to_tf32(w[((int64_t)n * cin + ch) * 9 + tap]) : 0.f;
 }
 
-template <bool UPS, bool TILED>
-int launch_tap_conv(const float* x, const float* wpacked, const float* bias, float* out, const TapConvShape& sh, cudaStream_t s) {
+template <bool UPS, bool TILED, bool WTMA, bool FULL>
+int launch_tap_conv(const CUtensorMap& map, const float* x, const float* wpacked, const float* bias, float* out, const TapConvShape& sh, cudaStream_t s) {
     static PerDeviceOnce done;
-    auto kern = tap_conv3x3_kernel<UPS, TILED>;
+    auto kern = tap_conv3x3_kernel<UPS, TILED, WTMA, FULL>;
     int dev = 0;
     cudaGetDevice(&dev);
     if (!done.test(dev)) {
@@ -328,7 +445,7 @@ int launch_tap_conv(const float* x, const float* wpacked, const float* bias, flo
         done.set(dev);
     }
     const int ctas = std::min(sh.ntiles, sm_count());
-    kern<<<ctas, TC_THREADS, TC_SMEM, s>>>(x, wpacked, bias, out, sh);
+    kern<<<ctas, TC_THREADS, TC_SMEM, s>>>(map, x, wpacked, bias, out, sh);
     count_launch();
     return finish_launch();
 }
@@ -347,7 +464,7 @@ extern "C" int sstem_tap_conv3x3_pack_weights(const float* weight, float* packed
     if (!aligned4(weight) || !aligned16(packed)) return SSTEM_E_ALIGN;
     DeviceGuard guard(packed);
     if (guard.err) return guard.err;
-    const int total = 9 * TC_CHUNKS * TC_N * 4;
+    const int total = (int)(TC_W_BYTES / 4);
     tap_conv3x3_pack_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(weight, packed, cin, cout);
     count_launch();
     return finish_launch();
@@ -377,6 +494,21 @@ extern "C" int sstem_tap_conv3x3(const float* x, const float* packed_weight, con
     sh.ry = sh.H > 1 ? (float)(sh.h - 1) / (float)(sh.H - 1) : 0.f;
     sh.rx = sh.W > 1 ? (float)(sh.w - 1) / (float)(sh.W - 1) : 0.f;
     cudaStream_t s = (cudaStream_t)stream;
-    if (ups) return tiled ? launch_tap_conv<true, true>(x, packed_weight, bias, out, sh, s) : launch_tap_conv<true, false>(x, packed_weight, bias, out, sh, s);
-    return tiled ? launch_tap_conv<false, true>(x, packed_weight, bias, out, sh, s) : launch_tap_conv<false, false>(x, packed_weight, bias, out, sh, s);
+    CUtensorMap map;
+    memset(&map, 0, sizeof(map));
+    if (ups) {
+        // the half-resolution source window by TMA: box {12 columns, 11 rows, 28 channels}, zero fill past the edges (never blended in)
+        const int64_t dims[4] = {w, h, cin, B}, strides[4] = {1, w, h * w, (int64_t)cin * h * w};
+        const int box[4] = {TC_WIN_W, TC_WIN_H, TC_WIN_GROUP_CH, 1};   // 12 x 11 x 28
+        const bool wtma = (w % 4 == 0) && make_map_f32(&map, x, 4, dims, strides, box);
+        const bool full = cin > 48;
+        if (wtma && full) return tiled ? launch_tap_conv<true, true, true, true>(map, x, packed_weight, bias, out, sh, s)
+                                       : launch_tap_conv<true, false, true, true>(map, x, packed_weight, bias, out, sh, s);
+        if (wtma) return tiled ? launch_tap_conv<true, true, true, false>(map, x, packed_weight, bias, out, sh, s)
+                               : launch_tap_conv<true, false, true, false>(map, x, packed_weight, bias, out, sh, s);
+        return tiled ? launch_tap_conv<true, true, false, false>(map, x, packed_weight, bias, out, sh, s)
+                     : launch_tap_conv<true, false, false, false>(map, x, packed_weight, bias, out, sh, s);
+    }
+    return tiled ? launch_tap_conv<false, true, false, false>(map, x, packed_weight, bias, out, sh, s)
+                 : launch_tap_conv<false, false, false, false>(map, x, packed_weight, bias, out, sh, s);
 }

@@ -17,15 +17,15 @@ def _stream_ptr(t: torch.Tensor) -> int:
 
 
 def pack_tap_conv_weight(weight: torch.Tensor) -> torch.Tensor:
-    """``Conv2d.weight`` ``[cout<=64, cin<=56, 3, 3]`` -> the kernel's resident image (126 KB, TF32-rounded).  Pack once per
+    """``Conv2d.weight`` ``[cout<=64, cin<=52, 3, 3]`` -> the kernel's resident image (118 KB, TF32-rounded).  Pack once per
     layer, reuse for every call."""
     if weight.is_cuda == False:
         raise NotImplementedError()
     if weight.dtype != torch.float32 or weight.dim() != 4 or tuple(weight.shape[2:]) != (3, 3):
         raise TypeError("pack_tap_conv_weight: float32 [cout, cin, 3, 3] required")
     cout, cin = weight.shape[:2]
-    if cin > 56 or cout > 64:
-        raise ValueError("pack_tap_conv_weight: cin <= 56 and cout <= 64 required")
+    if cin > 52 or cout > 64:
+        raise ValueError("pack_tap_conv_weight: cin <= 52 and cout <= 64 required")
     lib = _lib.load()
     packed = torch.empty(lib.sstem_tap_conv3x3_packed_elems(), dtype=torch.float32, device=weight.device)
     code = lib.sstem_tap_conv3x3_pack_weights(weight.contiguous().data_ptr(), packed.data_ptr(), cin, cout, _stream_ptr(weight))

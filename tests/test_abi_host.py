@@ -166,9 +166,9 @@ def test_argument_errors_of_the_section_8f_entry_points(built_lib):
     assert lib.sstem_sections_to_input(p, p, p, 1, 4, 4, -1, None) == -2
     assert lib.sstem_prediction_to_u8(p, None, 1, 4, 4, 0, None) == -1
     assert lib.sstem_prediction_to_u8(p + 1, p, 1, 4, 4, 0, None) == -3
-    assert lib.sstem_tap_conv3x3_packed_elems() == 9 * 14 * 64 * 4
+    assert lib.sstem_tap_conv3x3_packed_elems() == 9 * 13 * 64 * 4 + 64 * 4
     assert lib.sstem_tap_conv3x3_pack_weights(None, p, 51, 51, None) == -1
-    assert lib.sstem_tap_conv3x3_pack_weights(p, p, 57, 51, None) == -2                           # cin <= 56
+    assert lib.sstem_tap_conv3x3_pack_weights(p, p, 53, 51, None) == -2                           # cin <= 52
     assert lib.sstem_tap_conv3x3(p, p, None, None, 1, 51, 51, 4, 4, 0, None) == -1
     assert lib.sstem_tap_conv3x3(p, p, None, p, 1, 51, 65, 4, 4, 0, None) == -2                   # cout <= 64
     assert lib.sstem_tap_conv3x3(p, p, None, p, 1, 51, 32, 4, 4, 2, None) == -2                   # tiled: 51 taps only
@@ -189,7 +189,7 @@ def test_section_8f_host_mirrors_refuse_to_run_without_cuda(built_lib):
     with pytest.raises(pkg.SstemError):
         pkg.sff_sim.gen_flow(8, 8, 1.0, 0.0)
     with pytest.raises(NotImplementedError):
-        pkg.tap_conv3x3(torch.zeros((1, 51, 4, 4)), torch.zeros(32256), cin=51, cout=51)
+        pkg.tap_conv3x3(torch.zeros((1, 51, 4, 4)), torch.zeros(30208), cin=51, cout=51)
     with pytest.raises(NotImplementedError):
         pkg.pack_tap_conv_weight(torch.zeros((51, 51, 3, 3)))
 

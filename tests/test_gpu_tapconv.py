@@ -47,7 +47,7 @@ def test_reference_model_layer(golden_dir=GOLDEN):
 
 @pytest.mark.parametrize("B,cin,cout,h,w,ups", [
     (1, 51, 51, 8, 4, True), (2, 51, 51, 13, 9, True), (1, 51, 51, 16, 8, False), (1, 51, 51, 37, 29, False),
-    (1, 8, 16, 5, 7, True), (1, 3, 5, 9, 6, False), (1, 56, 64, 6, 6, True), (2, 17, 33, 20, 11, False),
+    (1, 8, 16, 5, 7, True), (1, 3, 5, 9, 6, False), (1, 52, 64, 6, 6, True), (1, 52, 64, 6, 5, True), (2, 17, 33, 20, 11, False),
     (1, 51, 51, 1, 1, True), (1, 51, 51, 1, 1, False), (1, 4, 8, 2, 33, True),
 ])
 def test_small_and_ragged_shapes(B, cin, cout, h, w, ups):
