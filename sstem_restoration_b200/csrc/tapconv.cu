@@ -25,7 +25,11 @@
 #include <algorithm>
 
 #include "common.cuh"
-#include "tma.cuh"
+#include "tma.cuh"   // mbar_fence_init
+
+#ifndef SSTEM_TC_DIAG
+#define SSTEM_TC_DIAG 0                                    // kernel-tuning experiments: 1 = no blend, 2 = no output stores, 4 = no MMAs
+#endif
 
 namespace sstem {
 namespace {
@@ -67,18 +71,18 @@ struct TapConvShape {
     float ry, rx;                                          // align_corners scales (in - 1) / (out - 1)
 };
 
-// a wait that cannot hang the device: a protocol error traps (the launch fails loudly) instead of spinning for ever
+// a wait that cannot hang the device: a protocol error traps (the launch fails loudly) instead of spinning for ever.
+// try_wait suspends the thread in hardware for up to the hinted time, so a waiting role issues next to nothing.
 __device__ __forceinline__ void tc_wait(unsigned bar, unsigned parity) {
     unsigned ok;
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     if (ok) return;
-    const long long t0 = clock64();
-    for (;;) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    for (unsigned spins = 0;; ++spins) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity), "r"(100000u) : "memory");
         if (ok) return;
-        if (clock64() - t0 > 4000000000ll) __trap();       // ~2 s
+        if (spins > 4000000u) __trap();                    // seconds, whatever the hint does: a deadlock, not a slow tile
     }
 }
 __device__ __forceinline__ void tc_arrive(unsigned bar) {
@@ -110,20 +114,20 @@ __device__ __forceinline__ float lds_f32(unsigned addr) {
     return v;
 }
 
-// UPS: fold the x2 upsample into the producer.  WTMA (UPS only): the source window arrives by TMA (needs w % 4 == 0 and a
-// 16-byte aligned x); otherwise the producers gather it with plain loads.
-// FULL (WTMA only): cin is 49..52, i.e. all 13 chunks exist -- the blend loop then has no per-chunk checks.
-template <bool UPS, bool TILED, bool WTMA, bool FULL>
+// UPS: fold the x2 upsample into the producer.  WVEC (UPS only): w % 4 == 0 and x is 16-byte aligned, so the source
+// window is fetched with 16-byte loads; otherwise element by element.
+// FULL: cin is 49..52, i.e. all 13 chunks exist -- the MMA and blend loops then have no per-chunk checks.
+template <bool UPS, bool TILED, bool WVEC, bool FULL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-tap_conv3x3_kernel(const __grid_constant__ CUtensorMap map_x, const float* __restrict__ x, const float* __restrict__ wpacked,
+tap_conv3x3_kernel(const float* __restrict__ x, const float* __restrict__ wpacked,
                    const float* __restrict__ bias, float* __restrict__ out, const TapConvShape sh) {
     extern __shared__ __align__(128) unsigned char tc_smem_raw[];
     const unsigned base = ((unsigned)__cvta_generic_to_shared(tc_smem_raw) + 127u) & ~127u;
     unsigned char* gen = tc_smem_raw + (base - (unsigned)__cvta_generic_to_shared(tc_smem_raw));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // barriers: 0 weights, 1-2 a_full, 3-4 a_empty, 5-6 acc_full, 7-8 acc_empty, 9-10 win_full; the TMEM base address after them
+    // barriers: 0 weights, 1-2 a_full, 3-4 a_empty, 5-6 acc_full, 7-8 acc_empty; the TMEM base address after them
     const unsigned bar = base + TC_OFF_BAR;
-    const unsigned b_w = bar, b_afull = bar + 8, b_aempty = bar + 24, b_accfull = bar + 40, b_accempty = bar + 56, b_winfull = bar + 72;
+    const unsigned b_w = bar, b_afull = bar + 8, b_aempty = bar + 24, b_accfull = bar + 40, b_accempty = bar + 56;
     volatile unsigned* tmem_slot = reinterpret_cast<volatile unsigned*>(gen + TC_OFF_BAR + 96);
 
     if (tid == 0) {
@@ -133,7 +137,6 @@ tap_conv3x3_kernel(const __grid_constant__ CUtensorMap map_x, const float* __res
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b_aempty + 8 * s));
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b_accfull + 8 * s));
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b_accempty + 8 * s), "r"(TC_EPI_WARPS * 32));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b_winfull + 8 * s));
         }
         mbar_fence_init();
     }
@@ -206,6 +209,7 @@ tap_conv3x3_kernel(const __grid_constant__ CUtensorMap map_x, const float* __res
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             tc_arrive(b_accempty + 8 * as);                // the accumulator stage is free: the MMAs of tile it + 2 may start
             const int Y = Y0 + r, X = X0 + c;
+            if (SSTEM_TC_DIAG & 2) continue;
             if (TILED) {
                 // the 16 x 8 tile is two 8 x 8 blocks of the tile-major layout; a warp writes 32 consecutive floats per tap
                 // (cout == 51 here).  Pad pixels of an existing block (ragged H / W) are written as zeros.
@@ -234,43 +238,57 @@ tap_conv3x3_kernel(const __grid_constant__ CUtensorMap map_x, const float* __res
             }
         }
     } else if (warp == TC_EPI_WARPS) {
-        // ===================== MMA issuer: one lane
+        // ===================== MMA issuer.  The whole warp walks the loop, so every descriptor is warp-uniform arithmetic in
+        // uniform registers; one lane issues.  (Issued from inside an `if (lane == 0)` region the descriptors were
+        // per-thread values moved to uniform registers one by one: ~110 cycles per MMA, 3.4x the tensor core's own time.)
+        const unsigned tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
         if (lane == 0) {
             // weights: resident for the life of the CTA
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b_w), "r"(TC_W_BYTES) : "memory");
             for (int t = 0; t < 9; ++t)
                 tc_bulk_load(base + t * TC_W_TAP_BYTES, reinterpret_cast<const char*>(wpacked) + (size_t)t * TC_W_TAP_BYTES, TC_W_TAP_BYTES, b_w);
             tc_bulk_load(base + TC_W_ZERO_OFF, reinterpret_cast<const char*>(wpacked) + TC_W_ZERO_OFF, TC_N * 16, b_w);
-            tc_wait(b_w, 0);
-            // instruction descriptor: D = f32, A = B = tf32, both K-major, N = 64, M = 128
-            constexpr unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(TC_N >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
-            int it = 0;
-            for (int tile = blockIdx.x; tile < sh.ntiles; tile += gridDim.x, ++it) {   // (needs no coordinates)
-                const int s = it & 1;
-                const unsigned ph = (it >> 1) & 1;
-                tc_wait(b_accempty + 8 * s, ph ^ 1);       // accumulator stage drained by the epilogue (passes at once the first time)
-                tc_wait(b_afull + 8 * s, ph);              // patch written and fenced by the producers
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const unsigned a_base = base + TC_OFF_A + s * TC_A_BYTES;
-                const unsigned d_tmem = tmem + s * TC_N;
-                unsigned acc = 0;
-#pragma unroll 1
-                for (int tap = 0; tap < 9; ++tap) {
-                    const unsigned a_tap = a_base + ((tap / 3) * TC_PW + (tap % 3)) * 16;
-                    const unsigned w_tap = base + tap * TC_W_TAP_BYTES;
-                    for (int ks = 0; ks < sh.k_steps; ++ks) {
-                        const uint64_t da = tc_desc(a_tap + ks * 2 * TC_NPIX * 16, TC_NPIX * 16, TC_PW * 16);
-                        // the K-step's second weight chunk; past chunk 12 it is the zero chunk all taps share (the patch's chunk 13 is zero too)
-                        const unsigned w_lo = w_tap + ks * 2 * TC_N * 16;
-                        const unsigned w_lbo = (2 * ks + 1 < TC_WCHUNKS) ? TC_N * 16 : base + TC_W_ZERO_OFF - w_lo;
-                        const uint64_t db = tc_desc(w_lo, w_lbo, 128);
+        }
+        __syncwarp();
+        tc_wait(b_w, 0);
+        // instruction descriptor: D = f32, A = B = tf32, both K-major, N = 64, M = 128
+        constexpr unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(TC_N >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
+        // Descriptors differ only in their start-address field (units of 16 bytes, no carry out of the field: shared memory
+        // addresses are < 2^18): per tap + (dy * 10 + dx) pixels for the patch, + 13 chunks for the weights; per K-step
+        // + 2 chunks each.  The last K-step's second weight chunk is the zero chunk all taps share: its leading-byte
+        // offset field is (zero chunk - chunk 12 of the tap) instead of one chunk.
+        const uint64_t db0 = tc_desc(base, TC_N * 16, 128);
+        const int k_steps = FULL ? TC_CHUNKS / 2 : sh.k_steps;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < sh.ntiles; tile += gridDim.x, ++it) {   // (needs no coordinates)
+            const int s = it & 1;
+            const unsigned ph = (it >> 1) & 1;
+            tc_wait(b_accempty + 8 * s, ph ^ 1);           // accumulator stage drained by the epilogue (passes at once the first time)
+            tc_wait(b_afull + 8 * s, ph);                  // patch written and fenced by the producers
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t da0 = (SSTEM_TC_DIAG & 32) ? tc_desc(base + TC_OFF_A, 3072, 256)       // timing experiment: 128-byte aligned core matrices
+                                                      : tc_desc(base + TC_OFF_A + s * TC_A_BYTES, TC_NPIX * 16, TC_PW * 16);
+            const unsigned d_tmem = tmem_u + s * TC_N;
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+                for (int ks = 0; ks < TC_CHUNKS / 2; ++ks) {
+                    if ((SSTEM_TC_DIAG & 4) || ks >= k_steps) break;
+                    const uint64_t da = (SSTEM_TC_DIAG & 32) ? da0 + (uint64_t)((tap / 3) * 16 + ks * 2 * 192)
+                                      : (SSTEM_TC_DIAG & 16) ? da0 + (uint64_t)((tap / 3) * TC_PW + ks * 2 * TC_NPIX)
+                                                             : da0 + (uint64_t)((tap / 3) * TC_PW + (tap % 3) + ks * 2 * TC_NPIX);
+                    uint64_t db = db0 + (uint64_t)((tap * TC_W_TAP_BYTES + ks * 2 * TC_N * 16) >> 4);
+                    if (2 * ks + 1 >= TC_WCHUNKS)
+                        db += (uint64_t)(((TC_W_ZERO_OFF - tap * TC_W_TAP_BYTES - ks * 2 * TC_N * 16) >> 4) - TC_N) << 16;
+                    if (lane == 0)
                         asm volatile(
                             "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                             "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                            ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
-                        acc = 1;
-                    }
+                            ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"((unsigned)((tap | ks) != 0)) : "memory");
                 }
+            }
+            __syncwarp();
+            if (lane == 0) {
                 tc_commit(b_aempty + 8 * s);               // patch stage may be overwritten
                 tc_commit(b_accfull + 8 * s);              // accumulator complete
             }
@@ -288,50 +306,67 @@ tap_conv3x3_kernel(const __grid_constant__ CUtensorMap map_x, const float* __res
         auto window_origin = [&](int Y0, int X0, int& sy0, int& sx0) {
             // PyTorch upsample_bilinear2d, align_corners = True: source index = scale * dst in float, cut to int
             sy0 = (int)(sh.ry * (float)max(Y0 - 1, 0));
-            sx0 = (int)(sh.rx * (float)max(X0 - 1, 0)) & ~3;       // 16-byte aligned box start
+            sx0 = (int)(sh.rx * (float)max(X0 - 1, 0)) & ~3;       // 16-byte aligned rows
         };
-        // WTMA: one elected thread asks the TMA unit for the two channel groups of a tile's window
-        auto issue_window = [&](const TileIter& t, int g) {
-            int sy0, sx0;
-            const int b = t.b;
-            window_origin(t.ty * TC_TH, t.tx * TC_TW, sy0, sx0);
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b_winfull + 8 * g), "r"(TC_WIN_GROUP_BYTES) : "memory");
-            asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-                         ::"r"(win + g * TC_WIN_GROUP_PITCH), "l"(reinterpret_cast<uint64_t>(&map_x)), "r"(b_winfull + 8 * g),
-                           "r"(sx0), "r"(sy0), "r"(g * TC_WIN_GROUP_CH), "r"(b) : "memory");
-        };
-        // !WTMA: the window of tile i + 1 is gathered into registers while tile i's patch is computed
-        constexpr int NFILL = WTMA ? 1 : (TC_MAXC * TC_WIN_CH + TC_PROD_THREADS - 1) / TC_PROD_THREADS;   // 18
-        float pre[NFILL];
-        auto load_window = [&](const TileIter& t) {
-            int sy0, sx0;
-            const int b = t.b;
-            window_origin(t.ty * TC_TH, t.tx * TC_TW, sy0, sx0);
-            const float* xb = x + (int64_t)b * sh.cin * src_plane;
+        // The window of tile i + 1 is fetched into registers while tile i's patch is computed (a whole tile of lookahead hides
+        // the L2 / DRAM latency) and moves to shared memory once every producer is done reading the previous window.  A TMA
+        // box per channel group was tried first: its 48-byte rows cost ~2 us per box and shared memory has no room for a
+        // second window, so half of that latency stayed exposed (0.85 ms vs the register prefetch).
+        constexpr int ROW4 = TC_WIN_W / 4;                 // 16-byte pieces per window row: 3
+        constexpr int NFILL = WVEC ? (TC_MAXC * TC_WIN_H * ROW4 + TC_PROD_THREADS - 1) / TC_PROD_THREADS      // 5 x float4
+                                   : (TC_MAXC * TC_WIN_CH + TC_PROD_THREADS - 1) / TC_PROD_THREADS;          // 18 x float
+        float4 pre4[WVEC ? NFILL : 1];
+        float pre[WVEC ? 1 : NFILL];
+        // WVEC: which 16-byte piece this thread fetches in round k does not depend on the tile: its channel offset (elements;
+        // the host checks cin * h * w < 2^31), window row and column piece are computed once
+        int f_choff[WVEC ? NFILL : 1], f_wy[WVEC ? NFILL : 1], f_c4[WVEC ? NFILL : 1], f_dst[WVEC ? NFILL : 1];
+        if (WVEC) {
 #pragma unroll
             for (int k = 0; k < NFILL; ++k) {
                 const int i = ptid + k * TC_PROD_THREADS;
-                const int ch = i / TC_WIN_CH, p = i - ch * TC_WIN_CH;
-                const int wy = p / TC_WIN_W, wx = p - wy * TC_WIN_W;
-                const int gy = min(sy0 + wy, sh.h - 1), gx = min(sx0 + wx, sh.w - 1);
-                pre[k] = ch < sh.cin ? __ldg(xb + (int64_t)ch * src_plane + (int64_t)gy * sh.w + gx) : 0.f;
+                const int ch = i / (TC_WIN_H * ROW4), rem = i - ch * (TC_WIN_H * ROW4);
+                f_wy[k] = rem / ROW4;
+                f_c4[k] = 4 * (rem - f_wy[k] * ROW4);
+                f_choff[k] = ch < sh.cin ? ch * (int)src_plane : -1;
+                const int g = ch >= TC_WIN_GROUP_CH ? 1 : 0;
+                f_dst[k] = ch < TC_MAXC ? (int)(g * TC_WIN_GROUP_PITCH + (ch - g * TC_WIN_GROUP_CH) * (TC_WIN_CH * 4) + rem * 16) : -1;
+            }
+        }
+        auto load_window = [&](const TileIter& t) {
+            int sy0, sx0;
+            window_origin(t.ty * TC_TH, t.tx * TC_TW, sy0, sx0);
+            const float* xb = x + (int64_t)t.b * sh.cin * src_plane;
+#pragma unroll
+            for (int k = 0; k < NFILL; ++k) {
+                const int i = ptid + k * TC_PROD_THREADS;
+                if (WVEC) {
+                    const int gy = min(sy0 + f_wy[k], sh.h - 1), gx = sx0 + f_c4[k];   // columns past the edge are never blended in
+                    pre4[k] = (f_choff[k] >= 0 && gx < sh.w) ? __ldg(reinterpret_cast<const float4*>(xb + (f_choff[k] + gy * sh.w + gx)))
+                                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+                } else {
+                    const int ch = i / TC_WIN_CH, p = i - ch * TC_WIN_CH;
+                    const int wy = p / TC_WIN_W, wx = p - wy * TC_WIN_W;
+                    const int gy = min(sy0 + wy, sh.h - 1), gx = min(sx0 + wx, sh.w - 1);
+                    pre[k] = ch < sh.cin ? __ldg(xb + (int64_t)ch * src_plane + (int64_t)gy * sh.w + gx) : 0.f;
+                }
             }
         };
         auto store_window = [&]() {
 #pragma unroll
             for (int k = 0; k < NFILL; ++k) {
                 const int i = ptid + k * TC_PROD_THREADS;
-                const int ch = i / TC_WIN_CH, p = i - ch * TC_WIN_CH;
-                const int g = ch >= TC_WIN_GROUP_CH ? 1 : 0;
-                if (ch < TC_MAXC) win_gen[g * (TC_WIN_GROUP_PITCH / 4) + (ch - g * TC_WIN_GROUP_CH) * TC_WIN_CH + p] = pre[k];
+                if (WVEC) {
+                    if (f_dst[k] >= 0) sts128(win + f_dst[k], pre4[k].x, pre4[k].y, pre4[k].z, pre4[k].w);
+                } else {
+                    const int ch = i / TC_WIN_CH, p = i - ch * TC_WIN_CH;
+                    const int g = ch >= TC_WIN_GROUP_CH ? 1 : 0;
+                    if (ch < TC_MAXC) win_gen[g * (TC_WIN_GROUP_PITCH / 4) + (ch - g * TC_WIN_GROUP_CH) * TC_WIN_CH + p] = pre[k];
+                }
             }
         };
         TileIter ti = first_tile(), tn = ti;               // this tile and the next one of this CTA
         advance(tn);
-        if (UPS && ti.tile < sh.ntiles) {
-            if (WTMA) { if (ptid == 0) { issue_window(ti, 0); issue_window(ti, 1); } }
-            else load_window(ti);
-        }
+        if (UPS && ti.tile < sh.ntiles) load_window(ti);
         // per-thread constants of the blend: chunk parity folded into the base addresses, so every shared-memory offset
         // below is an immediate
         const unsigned half_win = half * 4 * (TC_WIN_CH * 4), half_dst = half * TC_NPIX * 16;
@@ -356,17 +391,14 @@ tap_conv3x3_kernel(const __grid_constant__ CUtensorMap map_x, const float* __res
                 const float wa = h0l * w0l, wb = h0l * w1l, wc = h1l * w0l, wd = h1l * w1l;
                 const int cell = min(max(h1 - sy0, 0), TC_WIN_H - 2) * TC_WIN_W + min(max(w1 - sx0, 0), TC_WIN_W - 2);
                 const unsigned a00 = win + cell * 4 + half_win, a01 = a00 + w1p * 4, a10 = a00 + h1p * TC_WIN_W * 4, a11 = a10 + w1p * 4;
-                if (!WTMA) {
-                    asm volatile("bar.sync 2, %0;" ::"n"(TC_PROD_THREADS) : "memory");   // everyone is done reading the previous window
-                    store_window();
-                    asm volatile("bar.sync 2, %0;" ::"n"(TC_PROD_THREADS) : "memory");
-                    if (has_next) load_window(tn);
-                }
+                asm volatile("bar.sync 2, %0;" ::"n"(TC_PROD_THREADS) : "memory");   // everyone is done reading the previous window
+                store_window();
+                asm volatile("bar.sync 2, %0;" ::"n"(TC_PROD_THREADS) : "memory");
+                if (has_next) load_window(tn);
+                tc_wait(b_aempty + 8 * s, ph ^ 1);         // the MMAs that read this patch stage two tiles ago are complete
 #pragma unroll
                 for (int g = 0; g < TC_WIN_GROUPS; ++g) {
-                    if (WTMA) tc_wait(b_winfull + 8 * g, it & 1);
-                    if (g == 0) tc_wait(b_aempty + 8 * s, ph ^ 1);     // the MMAs that read this patch stage two tiles ago are complete
-                    if (has_pixel) {
+                    if (has_pixel && !(SSTEM_TC_DIAG & 1)) {
                         // this thread's chunks of the group: 7 g + half + 2 k.  With 13 chunks (cin 49..52, FULL) that is
                         // k < 3, plus k = 3 for the even chunks of group 0; otherwise each chunk is checked against cin.
 #pragma unroll
@@ -387,10 +419,6 @@ tap_conv3x3_kernel(const __grid_constant__ CUtensorMap map_x, const float* __res
                                 sts128(dst, 0.f, 0.f, 0.f, 0.f);
                             }
                         }
-                    }
-                    if (WTMA) {
-                        asm volatile("bar.sync 2, %0;" ::"n"(TC_PROD_THREADS) : "memory");   // the group's window has been read by everyone
-                        if (ptid == 0 && has_next) issue_window(tn, g);
                     }
                 }
             } else {
@@ -434,10 +462,10 @@ __global__ void tap_conv3x3_pack_kernel(const float* __restrict__ w, float* __re
     packed[i] = (n < cout && ch < cin) ? to_tf32(w[((int64_t)n * cin + ch) * 9 + tap]) : 0.f;
 }
 
-template <bool UPS, bool TILED, bool WTMA, bool FULL>
-int launch_tap_conv(const CUtensorMap& map, const float* x, const float* wpacked, const float* bias, float* out, const TapConvShape& sh, cudaStream_t s) {
+template <bool UPS, bool TILED, bool WVEC, bool FULL>
+int launch_tap_conv(const float* x, const float* wpacked, const float* bias, float* out, const TapConvShape& sh, cudaStream_t s) {
     static PerDeviceOnce done;
-    auto kern = tap_conv3x3_kernel<UPS, TILED, WTMA, FULL>;
+    auto kern = tap_conv3x3_kernel<UPS, TILED, WVEC, FULL>;
     int dev = 0;
     cudaGetDevice(&dev);
     if (!done.test(dev)) {
@@ -445,7 +473,7 @@ int launch_tap_conv(const CUtensorMap& map, const float* x, const float* wpacked
         done.set(dev);
     }
     const int ctas = std::min(sh.ntiles, sm_count());
-    kern<<<ctas, TC_THREADS, TC_SMEM, s>>>(map, x, wpacked, bias, out, sh);
+    kern<<<ctas, TC_THREADS, TC_SMEM, s>>>(x, wpacked, bias, out, sh);
     count_launch();
     return finish_launch();
 }
@@ -488,27 +516,22 @@ extern "C" int sstem_tap_conv3x3(const float* x, const float* packed_weight, con
     sh.tiles_x = (sh.W + TC_TW - 1) / TC_TW;
     sh.tiles_y = (sh.H + TC_TH - 1) / TC_TH;
     const int64_t nt = (int64_t)sh.tiles_x * sh.tiles_y * B;
-    if (nt > INT32_MAX / 2) return SSTEM_E_SHAPE;
+    if (nt > INT32_MAX / 2 || (int64_t)cin * h * w > INT32_MAX) return SSTEM_E_SHAPE;
     sh.ntiles = (int)nt;
     sh.k_steps = (cin + 7) / 8;
     sh.ry = sh.H > 1 ? (float)(sh.h - 1) / (float)(sh.H - 1) : 0.f;
     sh.rx = sh.W > 1 ? (float)(sh.w - 1) / (float)(sh.W - 1) : 0.f;
     cudaStream_t s = (cudaStream_t)stream;
-    CUtensorMap map;
-    memset(&map, 0, sizeof(map));
+    const bool full = cin > 48;                            // all 13 channel chunks exist: the common (51-channel) case, no per-chunk checks
+#define SSTEM_TC_LAUNCH(UPS_, WVEC_)                                                                                       \
+    return full ? (tiled ? launch_tap_conv<UPS_, true, WVEC_, true>(x, packed_weight, bias, out, sh, s)                    \
+                         : launch_tap_conv<UPS_, false, WVEC_, true>(x, packed_weight, bias, out, sh, s))                  \
+                : (tiled ? launch_tap_conv<UPS_, true, WVEC_, false>(x, packed_weight, bias, out, sh, s)                   \
+                         : launch_tap_conv<UPS_, false, WVEC_, false>(x, packed_weight, bias, out, sh, s))
     if (ups) {
-        // the half-resolution source window by TMA: box {12 columns, 11 rows, 28 channels}, zero fill past the edges (never blended in)
-        const int64_t dims[4] = {w, h, cin, B}, strides[4] = {1, w, h * w, (int64_t)cin * h * w};
-        const int box[4] = {TC_WIN_W, TC_WIN_H, TC_WIN_GROUP_CH, 1};   // 12 x 11 x 28
-        const bool wtma = (w % 4 == 0) && make_map_f32(&map, x, 4, dims, strides, box);
-        const bool full = cin > 48;
-        if (wtma && full) return tiled ? launch_tap_conv<true, true, true, true>(map, x, packed_weight, bias, out, sh, s)
-                                       : launch_tap_conv<true, false, true, true>(map, x, packed_weight, bias, out, sh, s);
-        if (wtma) return tiled ? launch_tap_conv<true, true, true, false>(map, x, packed_weight, bias, out, sh, s)
-                               : launch_tap_conv<true, false, true, false>(map, x, packed_weight, bias, out, sh, s);
-        return tiled ? launch_tap_conv<true, true, false, false>(map, x, packed_weight, bias, out, sh, s)
-                     : launch_tap_conv<true, false, false, false>(map, x, packed_weight, bias, out, sh, s);
+        if ((w % 4 == 0) && aligned16(x)) { SSTEM_TC_LAUNCH(true, true); }
+        SSTEM_TC_LAUNCH(true, false);
     }
-    return tiled ? launch_tap_conv<false, true, false, false>(map, x, packed_weight, bias, out, sh, s)
-                 : launch_tap_conv<false, false, false, false>(map, x, packed_weight, bias, out, sh, s);
+    SSTEM_TC_LAUNCH(false, false);
+#undef SSTEM_TC_LAUNCH
 }
