@@ -474,6 +474,7 @@ def run_gpu_arm(args):
         configs = {}
         configs.update(run_c2_c4_sepconv(pkg, dev, fp32_peak, hbm))
         configs.update(run_c4_warps(pkg, dev, hbm))
+        configs["n2_tap_producer_2048"] = run_tap_producer(pkg, dev, peaks)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -740,6 +741,52 @@ def run_c4_warps(pkg, dev, hbm_gbs):
                      "gpix_per_s": round(n * n / (ms * 1e-3) / 1e9, 2), "l2": f"{nsets} rotating buffer sets ({nsets * 134} MB)"}
         del bufs
         torch.cuda.empty_cache()
+    return res
+
+
+def run_tap_producer(pkg, dev, peaks):
+    """SURVEY 8f N2, producer side, at config 4's size: the last two layers of a tap branch (upsample x2 -> Conv2d(51,51,3);
+    model_interp.py:18, 130-137) as the fused tcgen05 kernel writing tile-major taps, and the producer -> consumer chain
+    (two tap tensors -> sepconv_forward_tiled) with no [B,51,H,W] tensor in between.  Roofline: tensor-bound work, measured
+    against half the dense bf16 figure of MEASURED_PEAKS.json (TF32 runs at half the bf16 rate), burst value -- the
+    kernel is timed alone.  The library chain it replaces (F.interpolate -> cuDNN TF32 conv -> layout conversion) is timed
+    beside it by tools/bench_tapconv.py (profiles/tapconv_r2.md); bench.py runs none of torch's operators."""
+    import torch
+    n = 2048
+    gen = torch.Generator(device=dev).manual_seed(99)
+    nrot = 4                                                   # 4 x (53 MB in + 855 MB out) >> L2
+    xs = [torch.relu(torch.randn((1, 51, n // 2, n // 2), device=dev, generator=gen)) for _ in range(nrot)]
+    w = torch.randn((51, 51, 3, 3), device=dev, generator=gen) / 21.4
+    bias = 0.1 * torch.randn(51, device=dev, generator=gen)
+    packed = pkg.pack_tap_conv_weight(w)
+    outs = [None, None]
+    it = [0]
+
+    def step():
+        it[0] += 1
+        outs[it[0] & 1] = pkg.tap_conv3x3(xs[it[0] % nrot], packed, bias, upsample=True, tiled=True)
+    ms = _events_ms(step, 20, warm=5)
+    flop = 2.0 * 51 * 51 * 9 * n * n
+    tf32_peak = float(peaks.get("bf16_tflops", 2250.0)) / 2
+    res = {"ms_per_tap_tensor": round(ms, 4), "tflops_useful": round(flop / ms / 1e9, 1), "flop_per_pixel": 2 * 51 * 51 * 9,
+           "roofline": {"bound": "tensor", "achieved": round(flop / ms / 1e9, 1), "peak": round(tf32_peak, 1), "unit": "TFLOP/s",
+                        "frac": round(flop / ms / 1e9 / tf32_peak, 4),
+                        "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst) / 2: TF32 is half the bf16 rate" if "bf16_tflops" in peaks else "nominal 1125 TFLOP/s TF32 dense",
+                        "note": "useful flops only (51 of the 64 padded output channels, 51 of 56 padded input channels: the tensor core does 1.38x this)"},
+           "hbm_gb_per_s": round((51 * (n // 2) ** 2 + 51 * n * n) * 4 / ms / 1e6, 1),
+           "kernel": "tap_conv3x3_kernel<UPS, TILED>: tcgen05.mma kind::tf32 M128 N64 K8, accumulators in TMEM, upsample fused into the operand producer"}
+    # producer -> consumer without NCHW taps: two branches feed one sepconv forward
+    frame = torch.rand((1, 3, n + 50, n + 50), device=dev, generator=gen)
+
+    def chain():
+        v = pkg.tap_conv3x3(xs[0], packed, bias, upsample=True, tiled=True)
+        h = pkg.tap_conv3x3(xs[1], packed, bias, upsample=True, tiled=True)
+        return pkg.sepconv_forward_tiled(frame, v, h)
+    cms = _events_ms(chain, 10, warm=3)
+    res["chain_2_producers_1_sepconv_ms"] = round(cms, 4)
+    res["chain_mpix_per_s"] = round(n * n / cms / 1e3, 1)
+    del xs, outs
+    torch.cuda.empty_cache()
     return res
 
 
