@@ -5,8 +5,9 @@ sff_scripts_interp/model/model_interp.py:18, 34, 130-137), run on CPU (true fp32
     python tests/golden/make_tap_producer_golden.py
 
 `model_interp.py` is imported unmodified (see make_kpn_taps_golden.py for the import path trick).  IFNet(kernel_size=51) is
-built with torch.manual_seed(3) and run on a 64x64 pair of synthetic sections; hooks on `upconv51_1[6]` (the shared
-nn.Upsample) and `upconv51_1[7]` (the final Conv2d) capture what goes in and what comes out.  The forward stops at the
+built with torch.manual_seed(3) and run on a 64x64 pair of synthetic sections; hooks on `upconv51_1[6]` (the nn.Upsample
+all branches and the decoder share -- its last input before the conv runs is this branch's) and `upconv51_1[7]` (the
+final Conv2d) capture what goes in and what comes out.  The forward stops at the
 CPU sepconv call, which raises NotImplementedError like the reference's op.
 """
 import os
