@@ -785,6 +785,22 @@ def run_tap_producer(pkg, dev, peaks):
     cms = _events_ms(chain, 10, warm=3)
     res["chain_2_producers_1_sepconv_ms"] = round(cms, 4)
     res["chain_mpix_per_s"] = round(n * n / cms / 1e3, 1)
+    # the interpolation tail on tile-major taps against the fused tail on [1,51,H,W] taps (gray x3 sections, as config 5 feeds)
+    tiled = [pkg.tap_conv3x3(xs[i], packed, bias, upsample=True, tiled=True) for i in range(4)]
+    i1, i2 = (torch.rand((1, 1, n, n), device=dev, generator=gen).expand(1, 3, n, n).contiguous() for _ in range(2))
+    pkg.set_gray_replicated("assert")
+    try:
+        tms = _events_ms(lambda: pkg.interpolation_tail_tiled(i1, i2, *tiled), 10, warm=3)
+        del frame
+        nchw = [pkg.tap_conv3x3(xs[i], packed, bias, upsample=True, tiled=False) for i in range(4)]
+        fms = _events_ms(lambda: pkg.interpolation_tail(i1, i2, *nchw), 10, warm=3)
+    finally:
+        pkg.set_gray_replicated("off")
+    res["tail_tiled_taps_ms"] = round(tms, 4)
+    res["tail_fused_nchw_taps_ms"] = round(fms, 4)
+    res["tail_note"] = ("gray x3 sections: interpolation_tail_tiled = frame_mean_pad x2 + two one-plane persistent forwards on tile-major taps "
+                        "(second accumulates); interpolation_tail = the fused generation-1 kernel on [1,51,H,W] taps")
+    del tiled, nchw
     del xs, outs
     torch.cuda.empty_cache()
     return res

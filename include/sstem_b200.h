@@ -53,6 +53,8 @@ extern "C" {
  * gradients use t = (sum_c g_c) * in_0 (same value up to fp32 rounding).  51 taps only; ignored by
  * the grad_input path (its result differs per channel through grad_output). */
 #define SSTEM_SEPCONV_GRAY_REPLICATED 2u
+/* sstem_sepconv_forward_tiled only: output += result (the second frame of the interpolation tail); not with GRAY_REPLICATED */
+#define SSTEM_SEPCONV_ACCUMULATE 4u
 
 /*
  * out[b,c,y,x] = sum_{fy,fx} in[b,c,y+fy,x+fx] * v[b,fy,y,x] * h[b,fx,y,x]
@@ -287,6 +289,16 @@ int sstem_taps_to_tiled(const float* taps, float* tiled, int64_t B, int64_t H, i
 int sstem_sepconv_forward_tiled(const float* input, const float* vertical_tiled, const float* horizontal_tiled,
                                 float* output, int64_t B, int64_t C, int64_t H, int64_t W,
                                 int32_t K, uint32_t flags, void* stream);
+
+/*
+ * The one-plane frame the interpolation tail convolves when its taps are tile-major (mean_c sepconv(i_c) = sepconv(mean_c i_c);
+ * sff_scripts_interp/model/model_interp.py:46, 90-97):  out[b,0,Y,X] = mean_c frame[b,c,clamp(Y-pad),clamp(X-pad)], i.e.
+ * channel mean + nn.ReplicationPad2d(pad).  frame [B,C,H,W] with batch stride frame_bstride elements (a channel slice of the
+ * network input); out [B,1,H+2 pad,W+2 pad].  SSTEM_SEPCONV_GRAY_REPLICATED: the planes are identical copies, plane 0 is used.
+ * The tail is then two sstem_sepconv_forward_tiled calls on one-plane frames, the second with SSTEM_SEPCONV_ACCUMULATE.
+ */
+int sstem_frame_mean_pad(const float* frame, int64_t frame_bstride, float* out, int64_t B, int64_t C, int64_t H, int64_t W,
+                         int32_t pad, uint32_t flags, void* stream);
 
 /*
  * Tap producer (producer side): the last two layers of IFNet._kernel_module,

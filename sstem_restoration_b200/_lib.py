@@ -26,6 +26,7 @@ _c_p = ctypes.c_void_p
 SEPCONV_DEFAULT = 0
 SEPCONV_STRICT_ORDER = 1
 SEPCONV_GRAY_REPLICATED = 2
+SEPCONV_ACCUMULATE = 4
 TAPCONV_UPSAMPLE2X = 1
 TAPCONV_TILED = 2
 LAYOUT_NCHW = 0
@@ -40,7 +41,7 @@ EXPORTED_SYMBOLS = (
     "sstem_sepconv_forward", "sstem_sepconv_backward", "sstem_interp_tail_forward", "sstem_interp_tail_backward",
     "sstem_warp_forward", "sstem_warp_backward", "sstem_image_warp", "sstem_sff_degrade", "sstem_sff_contrast",
     "sstem_sections_to_input", "sstem_prediction_to_u8", "sstem_warp_stitch_u8", "sstem_warp_stitch_forward",
-    "sstem_taps_tiled_elems", "sstem_taps_to_tiled", "sstem_sepconv_forward_tiled",
+    "sstem_taps_tiled_elems", "sstem_taps_to_tiled", "sstem_sepconv_forward_tiled", "sstem_frame_mean_pad",
     "sstem_sepconv_forward_detect", "sstem_sepconv_backward_detect",
     "sstem_tap_conv3x3_packed_elems", "sstem_tap_conv3x3_pack_weights", "sstem_tap_conv3x3",
     "sstem_fp32_peak_probe", "sstem_launch_count", "sstem_abi_version", "sstem_error_string",
@@ -99,6 +100,8 @@ def load() -> ctypes.CDLL:
         lib.sstem_taps_to_tiled.restype = ctypes.c_int
         lib.sstem_sepconv_forward_tiled.argtypes = [_c_p, _c_p, _c_p, _c_p, _c_i64, _c_i64, _c_i64, _c_i64, _c_i32, _c_u32, _c_p]
         lib.sstem_sepconv_forward_tiled.restype = ctypes.c_int
+        lib.sstem_frame_mean_pad.argtypes = [_c_p, _c_i64, _c_p, _c_i64, _c_i64, _c_i64, _c_i64, _c_i32, _c_u32, _c_p]
+        lib.sstem_frame_mean_pad.restype = ctypes.c_int
         lib.sstem_sepconv_forward_detect.argtypes = [_c_p, _c_p, _c_p, _c_p, _c_i64, _c_i64, _c_i64, _c_i64, _c_i32, _c_u32, _c_p, _c_p]
         lib.sstem_sepconv_forward_detect.restype = ctypes.c_int
         lib.sstem_sepconv_backward_detect.argtypes = [_c_p] * 7 + [_c_i64] * 4 + [_c_i32, _c_u32, _c_p, _c_p]

@@ -12,7 +12,7 @@ namespace {
 // returns 0 on launch, > 0 CUDA error, -1000 when the path does not apply
 template <int CC, bool TILED>
 int launch_fwd_v3(const float* in, const float* v, const float* h, float* out,
-                  int64_t B, int C, int c0, int H, int W, int replicas, bool force, cudaStream_t s) {
+                  int64_t B, int C, int c0, int H, int W, int replicas, bool force, cudaStream_t s, bool accum = false) {
     if (!TILED && ((W & 3) || !aligned16(v) || !aligned16(h))) return -1000;
     if (TILED && (!aligned16(v) || !aligned16(h))) return SSTEM_E_ALIGN;
     const int64_t tiles_x = (W + V3_COLS * V3_WARPS - 1) / (V3_COLS * V3_WARPS), tiles_y = (H + F3_R - 1) / F3_R;
@@ -57,7 +57,7 @@ int launch_fwd_v3(const float* in, const float* v, const float* h, float* out,
         e = set_smem_once(kern, F3_SMEM, done);
         if (!e) {
             V3Shape sh{H, W, (int)tiles_x, (int)tiles_y, (int)(tiles_x * tiles_y * B), C, c0};
-            F3Tiled tl{TILED ? v : nullptr, TILED ? h : nullptr, (int)((W + 7) / 8), (int)((H + 7) / 8)};
+            F3Tiled tl{TILED ? v : nullptr, TILED ? h : nullptr, (int)((W + 7) / 8), (int)((H + 7) / 8), accum ? 1 : 0};
             const int ctas = (int)std::min<int64_t>(2 * (int64_t)sm_count(), (int64_t)sh.ntiles);
             kern<<<ctas, V3_WARPS * 32, F3_SMEM, s>>>(min, mv, mh, tl, out, counter, sh, replicas, g_gate.ptr, g_gate.want);
             count_launch();
@@ -131,19 +131,22 @@ extern "C" int sstem_sepconv_forward_tiled(const float* input, const float* vert
     if (!input || !vertical_tiled || !horizontal_tiled || !output) return SSTEM_E_NULL;
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || C > 65535 || H > (1 << 24) || W > (1 << 24)) return SSTEM_E_SHAPE;
     if (K != K51) return SSTEM_E_SHAPE;                    // the tiled layout is defined for the reference's 51 taps
-    if (flags & ~SSTEM_SEPCONV_GRAY_REPLICATED) return SSTEM_E_FLAG;
+    if (flags & ~(SSTEM_SEPCONV_GRAY_REPLICATED | SSTEM_SEPCONV_ACCUMULATE)) return SSTEM_E_FLAG;
+    // the replicated planes are written from one register: nothing to add them to
+    if ((flags & SSTEM_SEPCONV_GRAY_REPLICATED) && (flags & SSTEM_SEPCONV_ACCUMULATE) && C > 1) return SSTEM_E_FLAG;
     if (!aligned4(input) || !aligned4(output)) return SSTEM_E_ALIGN;
     DeviceGuard guard(output);
     if (guard.err) return guard.err;
     cudaStream_t s = (cudaStream_t)stream;
+    const bool accum = flags & SSTEM_SEPCONV_ACCUMULATE;
     int e = 0;
-    if ((flags & SSTEM_SEPCONV_GRAY_REPLICATED) && C > 1)
+    if ((flags & SSTEM_SEPCONV_GRAY_REPLICATED) && C > 1) {
         e = launch_fwd_v3<1, true>(input, vertical_tiled, horizontal_tiled, output, B, (int)C, 0, (int)H, (int)W, (int)C, true, s);
-    else {
+    } else {
         int c0 = 0;
         while (c0 < C && !e) {                             // channel chunks of 3, then single planes
-            if (C - c0 >= 3) { e = launch_fwd_v3<3, true>(input, vertical_tiled, horizontal_tiled, output, B, (int)C, c0, (int)H, (int)W, 1, true, s); c0 += 3; }
-            else { e = launch_fwd_v3<1, true>(input, vertical_tiled, horizontal_tiled, output, B, (int)C, c0, (int)H, (int)W, 1, true, s); c0 += 1; }
+            if (C - c0 >= 3) { e = launch_fwd_v3<3, true>(input, vertical_tiled, horizontal_tiled, output, B, (int)C, c0, (int)H, (int)W, 1, true, s, accum); c0 += 3; }
+            else { e = launch_fwd_v3<1, true>(input, vertical_tiled, horizontal_tiled, output, B, (int)C, c0, (int)H, (int)W, 1, true, s, accum); c0 += 1; }
         }
     }
     return e == -1000 ? SSTEM_E_SHAPE : e;

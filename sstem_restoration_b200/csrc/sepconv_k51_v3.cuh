@@ -453,6 +453,7 @@ struct F3Tiled {
     const float* v;                                        // tile-major vertical / horizontal taps (TILED only)
     const float* h;
     int tiles_x8, tiles_y8;                                // warp tiles per row / column of the tiled layout
+    int accum;                                             // add to the output instead of overwriting it (second frame of the interpolation tail)
 };
 template <int CC, bool TILED>
 __global__ void __launch_bounds__(V3_WARPS * 32, 2)
@@ -627,6 +628,7 @@ sepconv_fwd_k51_v3_kernel(const __grid_constant__ CUtensorMap map_in, const __gr
                 for (int j = 0; j < 2; ++j) {
                     const int p = 2 * g + j;
                     if (ty0 + p < sh.H) {
+                        if (tl.accum) val[j] += ob[(int64_t)p * sh.W];
                         ob[(int64_t)p * sh.W] = val[j];
                         // gray x3 shortcut: the input planes are identical copies, so are the outputs
                         for (int rc = 1; rc < replicas; ++rc) ob[(int64_t)rc * plane + (int64_t)p * sh.W] = val[j];

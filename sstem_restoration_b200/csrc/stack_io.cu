@@ -140,6 +140,43 @@ extern "C" int sstem_sections_to_input(const uint8_t* section_prev, const uint8_
     return finish_launch();
 }
 
+// mean over the channel planes + ReplicationPad2d(pad): the one-plane frame the tile-major interpolation tail convolves
+// (mean_c sepconv(i_c) = sepconv(mean_c i_c); model_interp.py:46, 90-97).  One thread = one padded pixel.
+namespace sstem {
+namespace {
+__global__ void __launch_bounds__(256)
+frame_mean_pad_kernel(const float* __restrict__ frame, int64_t bstride, float* __restrict__ out, int nplanes, float scale,
+                      int H, int W, int pad) {
+    const int OW = W + 2 * pad, OH = H + 2 * pad;
+    const int X = blockIdx.x * blockDim.x + threadIdx.x, Y = blockIdx.y;
+    const int64_t b = blockIdx.z;
+    if (X >= OW) return;
+    const int sy = min(max(Y - pad, 0), H - 1), sx = min(max(X - pad, 0), W - 1);
+    const float* p = frame + b * bstride + (int64_t)sy * W + sx;
+    float acc = __ldg(p);
+    for (int c = 1; c < nplanes; ++c) acc += __ldg(p + (int64_t)c * H * W);
+    out[(b * OH + Y) * (int64_t)OW + X] = nplanes > 1 ? acc * scale : acc;
+}
+}  // namespace
+}  // namespace sstem
+
+extern "C" int sstem_frame_mean_pad(const float* frame, int64_t frame_bstride, float* out, int64_t B, int64_t C, int64_t H,
+                                    int64_t W, int32_t pad, uint32_t flags, void* stream) {
+    if (!frame || !out) return SSTEM_E_NULL;
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || pad < 0 || B > 65535 || H + 2 * (int64_t)pad > 65535 || W + 2 * (int64_t)pad > INT32_MAX / 2 ||
+        frame_bstride < C * H * W)
+        return SSTEM_E_SHAPE;
+    if (flags & ~SSTEM_SEPCONV_GRAY_REPLICATED) return SSTEM_E_FLAG;
+    if (!aligned4(frame) || !aligned4(out)) return SSTEM_E_ALIGN;
+    DeviceGuard guard(out);
+    if (guard.err) return guard.err;
+    const int nplanes = (flags & SSTEM_SEPCONV_GRAY_REPLICATED) ? 1 : (int)C;
+    dim3 grid((unsigned)((W + 2 * pad + 255) / 256), (unsigned)(H + 2 * pad), (unsigned)B);
+    frame_mean_pad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(frame, frame_bstride, out, nplanes, 1.0f / (float)nplanes, (int)H, (int)W, (int)pad);
+    count_launch();
+    return finish_launch();
+}
+
 extern "C" int sstem_prediction_to_u8(const float* pred, uint8_t* section, int64_t B, int64_t H, int64_t W, int32_t pad,
                                       void* stream) {
     if (!pred || !section) return SSTEM_E_NULL;

@@ -333,9 +333,12 @@ def taps_to_tiled(taps: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def sepconv_forward_tiled(input: torch.Tensor, vertical_tiled: torch.Tensor, horizontal_tiled: torch.Tensor) -> torch.Tensor:
+def sepconv_forward_tiled(input: torch.Tensor, vertical_tiled: torch.Tensor, horizontal_tiled: torch.Tensor, out=None,
+                          accumulate: bool = False) -> torch.Tensor:
     """``SeparableConvolution.apply(input, vertical, horizontal)`` with both tap tensors in the tile-major layout of
-    :func:`taps_to_tiled`; forward only; bit-identical to the [B,51,H,W] path.  Follows :func:`set_gray_replicated`."""
+    :func:`taps_to_tiled`; forward only; bit-identical to the [B,51,H,W] path.  Follows :func:`set_gray_replicated`.
+    ``out`` / ``accumulate``: write into (add to) an existing [B,C,H,W] tensor -- the second frame of the interpolation
+    tail (the general path only: the gray shortcut writes its replicas from one register)."""
     for t in (input, vertical_tiled, horizontal_tiled):
         if t.is_cuda == False:
             raise NotImplementedError()
@@ -346,12 +349,50 @@ def sepconv_forward_tiled(input: torch.Tensor, vertical_tiled: torch.Tensor, hor
     H, W = IH - 50, IW - 50
     want = (B, (H + 7) // 8, (W + 7) // 8, 51, 8, 8)
     assert tuple(vertical_tiled.shape) == want and tuple(horizontal_tiled.shape) == want, f"tiled taps must be {want}"
-    out = torch.empty((B, C, H, W), dtype=torch.float32, device=input.device)
+    if out is None:
+        if accumulate:
+            raise ValueError("sepconv_forward_tiled: accumulate needs an existing `out`")
+        out = torch.empty((B, C, H, W), dtype=torch.float32, device=input.device)
+    else:
+        assert tuple(out.shape) == (B, C, H, W) and out.dtype == torch.float32 and (out.is_contiguous() == True) and out.device == input.device
     if out.numel():
-        gray = _is_gray(input)
+        gray = (not accumulate) and _is_gray(input)
+        flags = (_lib.SEPCONV_GRAY_REPLICATED if gray else 0) | (_lib.SEPCONV_ACCUMULATE if accumulate else 0)
         code = _lib.load().sstem_sepconv_forward_tiled(input.data_ptr(), vertical_tiled.data_ptr(), horizontal_tiled.data_ptr(),
-                                                       out.data_ptr(), B, C, H, W, 51, _lib.SEPCONV_GRAY_REPLICATED if gray else 0,
-                                                       _stream_ptr(input))
+                                                       out.data_ptr(), B, C, H, W, 51, flags, _stream_ptr(input))
         if code:
             _lib.check(code, "sstem_sepconv_forward_tiled")
     return out
+
+
+def frame_mean_pad(frame: torch.Tensor, pad: int = 25, gray=None) -> torch.Tensor:
+    """``ReplicationPad2d(pad)(frame.mean(1, keepdim=True))`` in one launch: the one-plane frame the tile-major
+    interpolation tail convolves.  ``frame`` [B,C,H,W] (a channel slice ``x[:, :3]`` of the network input is taken as it
+    is); ``gray`` (default: :func:`set_gray_replicated` mode ``"assert"``): the planes are identical copies, plane 0 is used."""
+    if frame.is_cuda == False:
+        raise NotImplementedError()
+    if frame.dtype != torch.float32 or frame.dim() != 4:
+        raise TypeError("frame_mean_pad: float32 [B,C,H,W] required")
+    frame, bs = _frame_view(frame)
+    B, C, H, W = frame.shape
+    if gray is None:
+        gray = C > 1 and _GRAY == "assert"
+    out = torch.empty((B, 1, H + 2 * pad, W + 2 * pad), dtype=torch.float32, device=frame.device)
+    if out.numel():
+        code = _lib.load().sstem_frame_mean_pad(frame.data_ptr(), bs, out.data_ptr(), B, C, H, W, pad,
+                                                _lib.SEPCONV_GRAY_REPLICATED if gray else 0, _stream_ptr(frame))
+        if code:
+            _lib.check(code, "sstem_frame_mean_pad")
+    return out
+
+
+def interpolation_tail_tiled(i1, i2, k1v_tiled, k1h_tiled, k2v_tiled, k2h_tiled) -> torch.Tensor:
+    """:func:`interpolation_tail` for tap tensors in the tile-major layout (what :class:`ModuleTapProducer` emits): the whole
+    tail of ``IFNet.forward`` (model_interp.py:90-97) without a [B,51,H,W] tensor anywhere.  Forward only.
+
+    mean_c sepconv(pad(i_c)) = sepconv(pad(mean_c i_c)), so each frame is reduced to one replicate-padded plane
+    (:func:`frame_mean_pad`) and convolved by the persistent one-channel kernel; the second frame accumulates into the first
+    frame's output.  Returns [B,1,H,W]; agrees with :func:`interpolation_tail` to fp32 rounding."""
+    p2, p1 = frame_mean_pad(i2), frame_mean_pad(i1)
+    out = sepconv_forward_tiled(p2, k2v_tiled, k2h_tiled)
+    return sepconv_forward_tiled(p1, k1v_tiled, k1h_tiled, out=out, accumulate=True)

@@ -21,7 +21,7 @@ from typing import Callable, Dict, Optional
 import torch
 
 from . import _lib, shard
-from .sepconv import interpolation_tail
+from .sepconv import interpolation_tail, interpolation_tail_tiled
 from .stack_io import prediction_to_uint8, sections_to_input
 from .warp import SpatialTransformation
 
@@ -131,7 +131,7 @@ def restore_stack(stack: torch.Tensor, taps_fn: Callable, flow_fn: Optional[Call
     For every target k in 1..N-2 owned by this rank::
 
         x = sections_to_input(stack[k-1], stack[k+1])                # [1,6,H,W] float32, gray x3, /255
-        k1v, k1h, k2v, k2h = taps_fn(k, x)                           # the KPN (out of scope): four [1,51,H,W] tensors
+        k1v, k1h, k2v, k2h = taps_fn(k, x)                           # the KPN (out of scope): four [1,51,H,W] tensors, or tile-major
         interp = prediction_to_uint8(interpolation_tail(x[:, :3], x[:, 3:6], k1v, k1h, k2v, k2h))
         if flow_fn:                                                  # the correction module's flow net (out of scope)
             xk = sections_to_input(stack[k])                         # [1,3,H,W]: input_sff
@@ -178,7 +178,9 @@ def restore_stack(stack: torch.Tensor, taps_fn: Callable, flow_fn: Optional[Call
                     cache.request(kk)
             x = sections_to_input(cache.get(ka), cache.get(kb), 0)
             k1v, k1h, k2v, k2h = taps_fn(k, x)
-            interp = prediction_to_uint8(interpolation_tail(x[:, :3], x[:, 3:6], k1v, k1h, k2v, k2h), 0, out=local["interp"][i:i + 1])
+            # [1,51,H,W] taps: the fused tail; tile-major taps (6-D, what ModuleTapProducer writes): the tile-major tail
+            tail = interpolation_tail_tiled if k1v.dim() == 6 else interpolation_tail
+            interp = prediction_to_uint8(tail(x[:, :3], x[:, 3:6], k1v, k1h, k2v, k2h), 0, out=local["interp"][i:i + 1])
             if flow_fn is not None:
                 xk = sections_to_input(cache.get(k), None, 0)
                 # input_sff is a gray section replicated x3 (inference.py:129-131): its three warped planes are identical and

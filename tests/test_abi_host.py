@@ -166,6 +166,10 @@ def test_argument_errors_of_the_section_8f_entry_points(built_lib):
     assert lib.sstem_sections_to_input(p, p, p, 1, 4, 4, -1, None) == -2
     assert lib.sstem_prediction_to_u8(p, None, 1, 4, 4, 0, None) == -1
     assert lib.sstem_prediction_to_u8(p + 1, p, 1, 4, 4, 0, None) == -3
+    assert lib.sstem_frame_mean_pad(None, 48, p, 1, 3, 4, 4, 25, 0, None) == -1
+    assert lib.sstem_frame_mean_pad(p, 47, p, 1, 3, 4, 4, 25, 0, None) == -2                     # batch stride < C*H*W
+    assert lib.sstem_frame_mean_pad(p, 48, p, 1, 3, 4, 4, 25, 1, None) == -5
+    assert lib.sstem_sepconv_forward_tiled(p, p, p, p, 1, 3, 8, 8, 51, 2 | 4, None) == -5        # accumulate + gray replicas
     assert lib.sstem_tap_conv3x3_packed_elems() == 9 * 13 * 64 * 4 + 64 * 4
     assert lib.sstem_tap_conv3x3_pack_weights(None, p, 51, 51, None) == -1
     assert lib.sstem_tap_conv3x3_pack_weights(p, p, 53, 51, None) == -2                           # cin <= 52

@@ -119,6 +119,28 @@ def test_restore_stack_matches_the_op_by_op_expression():
     assert [p.shape[0] for p in parts] == [2, 1, 1] and torch.equal(torch.cat(parts), on_dev["interp"])
 
 
+def test_restore_stack_with_tile_major_taps_from_the_tap_producer():
+    """The N2 chain inside the stack loop: taps_fn returns tile-major taps (written by the tcgen05 tap producer from
+    half-resolution activations), restore_stack then takes the tile-major tail -- no [1,51,H,W] tensor anywhere.  Equal,
+    up to one uint8 count where fp32 rounding straddles the truncation, to the run on the same taps converted to NCHW."""
+    N, H, W = 5, 64, 96
+    stack = torch.from_numpy(np.stack([synth.em_section(H, W, 30 + i) for i in range(N)])).cuda()
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    acts = [torch.relu(torch.randn((1, 51, H // 2, W // 2), device="cuda", generator=gen)) for _ in range(4)]
+    prods = [pkg.ModuleTapProducer(tiled=True).cuda() for _ in range(4)]
+    plain = [pkg.ModuleTapProducer(tiled=False).cuda() for _ in range(4)]
+    for a, b in zip(prods, plain):
+        b.load_state_dict(a.state_dict())
+    pkg.set_gray_replicated("assert")                   # sections are gray x3 by construction (inference.py:71-74)
+    try:
+        tiled = pkg.restore_stack(stack, lambda k, x: [m(a) for m, a in zip(prods, acts)], None)["interp"]
+        nchw = pkg.restore_stack(stack, lambda k, x: [m(a) for m, a in zip(plain, acts)], None)["interp"]
+    finally:
+        pkg.set_gray_replicated("off")
+    assert tiled.shape == (N - 2, H, W) and tiled.dtype == torch.uint8
+    assert (tiled.int() - nchw.int()).abs().max().item() <= 1
+
+
 def _gather_worker(rank, world, port, q):
     import os
     import torch.distributed as dist

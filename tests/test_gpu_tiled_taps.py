@@ -81,3 +81,54 @@ def test_one_channel_persistent_kernel_vs_oracle_order():
     ci = inp[0:1, :, 500:500 + 82, 700:700 + 114].cpu().numpy()
     ref = oracle.sepconv_forward_reforder(ci, vs[0:1, :, 500:532, 700:764].cpu().numpy().copy(), hs[0:1, :, 500:532, 700:764].cpu().numpy().copy())
     assert np.abs(got - ref[0]).max() <= 1e-5
+
+
+@pytest.mark.parametrize("B,C,H,W,gray", [(1, 3, 64, 64, False), (2, 3, 37, 53, False), (1, 3, 40, 72, True), (1, 1, 24, 40, False)])
+def test_tiled_interpolation_tail_matches_fused_tail_and_oracle(B, C, H, W, gray):
+    """IFNet's tail (model_interp.py:90-97) on tile-major taps: frame_mean_pad + two one-plane tiled forwards, the second
+    accumulating -- against the fused NCHW tail and the oracle of the unfused expression."""
+    r = np.random.default_rng(B * 100 + H + W)
+    i1 = r.random((B, C, H, W), dtype=np.float32)
+    i2 = r.random((B, C, H, W), dtype=np.float32)
+    if gray:
+        i1[:, 1:] = i1[:, :1]
+        i2[:, 1:] = i2[:, :1]
+    taps = [cases.sepconv_inputs(B, 1, H, W, seed=40 + k, kind="unit")[1] for k in range(4)]       # k1v, k1h, k2v, k2h
+    ti1, ti2 = _cuda(i1, i2)
+    tt = _cuda(*taps)
+    pkg.set_gray_replicated("assert" if gray else "off")
+    try:
+        got = pkg.interpolation_tail_tiled(ti1, ti2, *(pkg.taps_to_tiled(t) for t in tt))
+        fused = pkg.interpolation_tail(ti1, ti2, *tt)
+    finally:
+        pkg.set_gray_replicated("off")
+    want = oracle.interp_tail_reference(i1, i2, *taps)
+    assert got.shape == (B, 1, H, W)
+    assert np.abs(got.cpu().numpy() - want).max() <= 1e-5
+    assert (got - fused).abs().max().item() <= 4e-6
+    # frame_mean_pad alone: ReplicationPad2d(25) of the channel mean, views of the x6 network input accepted as they are
+    x6 = torch.cat([ti1, ti2], 1) if C == 3 else None
+    if x6 is not None:
+        p = pkg.frame_mean_pad(x6[:, 3:6], 25, gray=False)
+        ref = torch.nn.functional.pad(ti2.mean(1, keepdim=True), (25, 25, 25, 25), mode="replicate")
+        assert (p - ref).abs().max().item() <= 2e-7
+
+
+def test_tiled_tail_at_stack_size_and_accumulate_flag():
+    """2048^2 (persistent kernel on every tile) and the accumulate flag on its own: out += forward."""
+    dev = "cuda"
+    gen = torch.Generator(device=dev).manual_seed(21)
+    H = W = 1024
+    i1 = torch.rand((1, 3, H, W), device=dev, generator=gen)
+    i2 = torch.rand((1, 3, H, W), device=dev, generator=gen)
+    taps = [torch.softmax(torch.randn((1, 51, H, W), device=dev, generator=gen), 1) for _ in range(4)]
+    tiled = [pkg.taps_to_tiled(t) for t in taps]
+    got = pkg.interpolation_tail_tiled(i1, i2, *tiled)
+    fused = pkg.interpolation_tail(i1, i2, *taps)
+    assert (got - fused).abs().max().item() <= 4e-6
+    p = pkg.frame_mean_pad(i1)
+    a = pkg.sepconv_forward_tiled(p, tiled[0], tiled[1])
+    b = pkg.sepconv_forward_tiled(p, tiled[0], tiled[1], out=a.clone(), accumulate=True)
+    assert torch.equal(b, a + a)
+    with pytest.raises(ValueError):
+        pkg.sepconv_forward_tiled(p, tiled[0], tiled[1], accumulate=True)
