@@ -459,11 +459,12 @@ def run_gpu_arm(args):
     fp32_peak, probe_mhz = pkg.fp32_peak_probe()
 
     # ---- config 5 (every rank takes part: strong scaling over the 98 targets) and its host-buffer form
-    c5 = c5_host = None
+    c5 = c5_host = c5_tiled = None
     if not args.no_stack:
         c5 = run_c5_stack(pkg, dev, rank, world, dist if world > 1 else None, args.sections, args.section_size)
         if e2e is not None:
             c5_host = run_c5_stack(pkg, dev, rank, world, dist if world > 1 else None, args.sections, args.section_size, to_host=True)
+        c5_tiled = run_c5_stack(pkg, dev, rank, world, dist if world > 1 else None, args.sections, args.section_size, tiled_taps=True)
 
     # ---- warp (configs 4 / 5), the other BASELINE configurations, section-8f rows: rank 0, beside the headline
     warp = run_warp(args, pkg, dev) if not args.no_warp else None
@@ -485,6 +486,8 @@ def run_gpu_arm(args):
         configs["c5_stack"] = c5
         if c5_host is not None:
             configs["c5_stack_host_out"] = c5_host
+        if c5_tiled is not None:
+            configs["c5_stack_tile_major_taps"] = c5_tiled
     if e2e is not None and c5_host is not None:
         e2e["e2e_u8"] = {"what": "config 5 through restore_stack with HOST buffers both ways: uint8 sections in pinned memory -> restored uint8 "
                                  "sections in pinned memory (1 byte per pixel up per section, 3 bytes per target down; every rank keeps its own targets)",
@@ -806,7 +809,7 @@ def run_tap_producer(pkg, dev, peaks):
     return res
 
 
-def run_c5_stack(pkg, dev, rank, world, dist, sections=100, size=4096, to_host=False):
+def run_c5_stack(pkg, dev, rank, world, dist, sections=100, size=4096, to_host=False, tiled_taps=False):
     """BASELINE config 5: a synthetic 100-section 4096x4096 stack, 98 targets (k-1, k+1) -> k
     (sff_scripts_interp/inference.py:69-70) through restore_stack: uint8 sections uploaded from pinned host memory
     inside the timed region, fused interpolation tail + flow warp + stitch per target, targets sharded contiguously
@@ -818,6 +821,8 @@ def run_c5_stack(pkg, dev, rank, world, dist, sections=100, size=4096, to_host=F
     H = W = size
     gen = torch.Generator(device=dev).manual_seed(4321 + rank)
     taps = [torch.softmax(torch.randn((1, K, H, W), device=dev, generator=gen), 1) for _ in range(4)]
+    if tiled_taps:                                            # the layout the tap producer writes: restore_stack then
+        taps = [pkg.taps_to_tiled(t) for t in taps]          # takes the tile-major tail
     flow_np, _ = synth.random_fold_flow(H, W, 555)
     flow = torch.from_numpy(np.ascontiguousarray(flow_np.transpose(2, 0, 1))[None]).to(dev).permute(0, 2, 3, 1)
     tile = synth.em_section(min(H, 1024), min(W, 1024), 0)
@@ -862,6 +867,7 @@ def run_c5_stack(pkg, dev, rank, world, dist, sections=100, size=4096, to_host=F
            "h2d_bytes_rank0": st["h2d_bytes"], "d2h_bytes_rank0": st["d2h_bytes"], "kernel_launches_rank0": st["kernel_launches"],
            "outputs": ("interp, warped, stitch: uint8, each rank downloads its own targets into pinned host memory (one async copy per target, no collective)"
                        if to_host else "interp, warped, stitch: uint8 [98,H,W] each, gathered to rank 0 (device memory)"),
+           "taps": "tile-major [1,H/8,W/8,51,8,8] (interpolation_tail_tiled)" if tiled_taps else "[1,51,H,W] (fused interpolation_tail)",
            "api": "sstem_restoration_b200.restore_stack(stack_u8_pinned, taps_fn, flow_fn, rank, world_size, dst=0)"}
     del taps, flow, stack, out
     torch.cuda.empty_cache()
