@@ -308,7 +308,7 @@ int sstem_frame_mean_pad(const float* frame, int64_t frame_bstride, float* out, 
  * folded into the operand producer, the result written [B,cout,H,W] or directly tile-major (SSTEM_TAPCONV_TILED, the
  * layout of sstem_sepconv_forward_tiled; cout must then be 51).
  *
- *   x       [B, cin, h, w]      cin <= 52
+ *   x       [B, cin, h, w]      cin <= 52, cin * h * w < 2^31
  *   weight  [cout, cin, 3, 3]   cout <= 64 (torch's Conv2d.weight); packed once by sstem_tap_conv3x3_pack_weights into
  *                               sstem_tap_conv3x3_packed_elems() floats ([tap][cin chunk of 4 < 13][64][4] + a zero chunk, rounded to TF32)
  *   bias    [cout] or NULL
