@@ -111,3 +111,29 @@ def test_module_loads_reference_conv_state_dict():
     x = torch.rand((1, 51, 8, 8), device="cuda")
     ref = conv.cuda()(torch.nn.functional.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True))
     assert (m(x) - ref).abs().max() <= 2.0 ** -9 * ref.abs().max()
+
+
+def test_large_image_against_fp32_library_convolution():
+    """1024^2 output (8192 tiles, 55 per CTA, image borders on all sides): the fp64 oracle is too slow here, so the comparison
+    is against torch's own fp32 (TF32 disabled) interpolate + conv2d on the same GPU, with the same TF32 bound."""
+    dev = "cuda"
+    gen = torch.Generator(device=dev).manual_seed(77)
+    x = torch.relu(torch.randn((1, 51, 512, 512), device=dev, generator=gen))
+    w = torch.randn((51, 51, 3, 3), device=dev, generator=gen) / 21.4
+    b = 0.1 * torch.randn(51, device=dev, generator=gen)
+    got = pkg.tap_conv3x3(x, pkg.pack_tap_conv_weight(w), b)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        up = torch.nn.functional.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True)
+        want = torch.nn.functional.conv2d(up, w, b, padding=1)
+        bound = torch.nn.functional.conv2d(up.abs(), w.abs(), b.abs(), padding=1)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    err = (got - want).abs()
+    assert bool((err <= 1.05 * 2.0 ** -10 * bound + 1e-5).all()), float((err / (2.0 ** -10 * bound + 1e-9)).max())
+    # typical error: well inside the bound (random signs), and no systematic offset
+    assert float(err.mean()) <= 0.1 * float((2.0 ** -10 * bound).mean())
+    assert abs(float((got - want).mean())) <= 1e-5
+    tiled = pkg.tap_conv3x3(x, pkg.pack_tap_conv_weight(w), b, tiled=True)
+    assert torch.equal(tiled, pkg.taps_to_tiled(got))
