@@ -78,11 +78,12 @@ __device__ __forceinline__ void tc_wait(unsigned bar, unsigned parity) {
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     if (ok) return;
-    for (unsigned spins = 0;; ++spins) {
+    const long long t0 = clock64();
+    for (unsigned spins = 1;; ++spins) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(bar), "r"(parity), "r"(100000u) : "memory");
+                     : "=r"(ok) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
         if (ok) return;
-        if (spins > 4000000u) __trap();                    // seconds, whatever the hint does: a deadlock, not a slow tile
+        if ((spins & 63u) == 0 && clock64() - t0 > 6000000000ll) __trap();   // ~3 s: a deadlock, not a slow tile
     }
 }
 __device__ __forceinline__ void tc_arrive(unsigned bar) {
