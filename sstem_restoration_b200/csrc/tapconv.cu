@@ -15,11 +15,13 @@
 //     descriptor of tap (dy, dx) is the same patch with its start address moved by (dy * 10 + dx) * 16 bytes,
 //     stride-byte-offset = one patch row (160 B), leading-byte-offset = one chunk (2880 B)
 //     (tools/microbench/umma_probe.cu checks exactly this encoding, shifted starts included);
-//   * the weights of all nine taps stay resident in shared memory for the life of the CTA (126 KB, one bulk copy);
-//   * warp roles: 4 epilogue warps (TMEM -> registers -> + bias -> global), 1 MMA warp (one lane issues), 6 producer
-//     warps (source window -> shared memory, bilinear blend with PyTorch's own index / weight expressions, round to
-//     TF32, write the patch); mbarriers between them, a persistent grid of one CTA per SM.
-// Shared memory bandwidth bounds the kernel (each MMA reads 4 KB of A and 2 KB of W for 65 536 FMAs); see DESIGN 4.11.
+//   * the weights of all nine taps stay resident in shared memory for the life of the CTA (118 KB, bulk copies);
+//   * warp roles: 4 epilogue warps (TMEM -> registers -> + bias -> global), 1 MMA warp (uniform descriptor arithmetic,
+//     one lane issues), 12 producer warps (thread = patch pixel x chunk parity: half-resolution source window ->
+//     shared memory, bilinear blend with ATen's index / weight expressions, round to TF32, write the patch);
+//     mbarriers between them, a persistent grid of one CTA per SM.
+// Shared memory bandwidth bounds the kernel (each MMA reads 4 KB of A and 2 KB of W for 65 536 FMAs); see DESIGN 4.11
+// and profiles/tapconv_r2.md.
 #include <string.h>
 
 #include <algorithm>
@@ -40,12 +42,13 @@ constexpr int TC_CHUNKS = TC_WCHUNKS + 1;                  // 14 patch chunks = 
 constexpr int TC_N = 64;                                   // output channels, padded (UMMA N)
 constexpr int TC_TH = 16, TC_TW = 8;                       // output tile: 128 pixels = UMMA M
 constexpr int TC_PH = TC_TH + 2, TC_PW = TC_TW + 2, TC_NPIX = TC_PH * TC_PW;   // 18 x 10 = 180
-// Half-resolution source window: 11 rows x up to 7 columns are used; a TMA box must start on a 16-byte boundary in
-// global memory, so the first column is rounded down to a multiple of 4 and 12 columns are loaded (48-byte rows).
+// Half-resolution source window: 11 rows x up to 7 columns are used; it is fetched with 16-byte loads (and, in an
+// earlier variant, by TMA, which has the same rule), so the first column is rounded down to a multiple of 4 and 12
+// columns are loaded (48-byte rows).
 constexpr int TC_WIN_H = 11, TC_WIN_W = 12;
 constexpr int TC_WIN_CH = TC_WIN_H * TC_WIN_W;             // 132 floats = 528 bytes per channel: [channel][row][column]
-constexpr int TC_WIN_GROUPS = 2, TC_WIN_GROUP_CH = 28;     // two channel groups (chunks 0-6, 7-12), loaded and consumed in turn
-constexpr unsigned TC_WIN_GROUP_BYTES = TC_WIN_GROUP_CH * TC_WIN_CH * 4;       // 14784: what one TMA box delivers
+constexpr int TC_WIN_GROUPS = 2, TC_WIN_GROUP_CH = 28;     // two channel groups (chunks 0-6, 7-12; a 128-byte aligned start each)
+constexpr unsigned TC_WIN_GROUP_BYTES = TC_WIN_GROUP_CH * TC_WIN_CH * 4;       // 14784
 constexpr unsigned TC_WIN_GROUP_PITCH = (TC_WIN_GROUP_BYTES + 127) / 128 * 128;   // 14848
 constexpr unsigned TC_W_TAP_BYTES = TC_WCHUNKS * TC_N * 16;                    // 13312
 constexpr unsigned TC_W_ZERO_OFF = 9 * TC_W_TAP_BYTES;                         // 119808: the zero chunk
