@@ -459,12 +459,13 @@ def run_gpu_arm(args):
     fp32_peak, probe_mhz = pkg.fp32_peak_probe()
 
     # ---- config 5 (every rank takes part: strong scaling over the 98 targets) and its host-buffer form
-    c5 = c5_host = c5_tiled = None
+    c5 = c5_host = c5_tiled = c5_prod = None
     if not args.no_stack:
         c5 = run_c5_stack(pkg, dev, rank, world, dist if world > 1 else None, args.sections, args.section_size)
         if e2e is not None:
             c5_host = run_c5_stack(pkg, dev, rank, world, dist if world > 1 else None, args.sections, args.section_size, to_host=True)
         c5_tiled = run_c5_stack(pkg, dev, rank, world, dist if world > 1 else None, args.sections, args.section_size, tiled_taps=True)
+        c5_prod = run_c5_stack(pkg, dev, rank, world, dist if world > 1 else None, args.sections, args.section_size, producer=True)
 
     # ---- warp (configs 4 / 5), the other BASELINE configurations, section-8f rows: rank 0, beside the headline
     warp = run_warp(args, pkg, dev) if not args.no_warp else None
@@ -488,6 +489,8 @@ def run_gpu_arm(args):
             configs["c5_stack_host_out"] = c5_host
         if c5_tiled is not None:
             configs["c5_stack_tile_major_taps"] = c5_tiled
+        if c5_prod is not None:
+            configs["c5_stack_with_tap_producers"] = c5_prod
     if e2e is not None and c5_host is not None:
         e2e["e2e_u8"] = {"what": "config 5 through restore_stack with HOST buffers both ways: uint8 sections in pinned memory -> restored uint8 "
                                  "sections in pinned memory (1 byte per pixel up per section, 3 bytes per target down; every rank keeps its own targets)",
@@ -809,7 +812,7 @@ def run_tap_producer(pkg, dev, peaks):
     return res
 
 
-def run_c5_stack(pkg, dev, rank, world, dist, sections=100, size=4096, to_host=False, tiled_taps=False):
+def run_c5_stack(pkg, dev, rank, world, dist, sections=100, size=4096, to_host=False, tiled_taps=False, producer=False):
     """BASELINE config 5: a synthetic 100-section 4096x4096 stack, 98 targets (k-1, k+1) -> k
     (sff_scripts_interp/inference.py:69-70) through restore_stack: uint8 sections uploaded from pinned host memory
     inside the timed region, fused interpolation tail + flow warp + stitch per target, targets sharded contiguously
@@ -823,6 +826,14 @@ def run_c5_stack(pkg, dev, rank, world, dist, sections=100, size=4096, to_host=F
     taps = [torch.softmax(torch.randn((1, K, H, W), device=dev, generator=gen), 1) for _ in range(4)]
     if tiled_taps:                                            # the layout the tap producer writes: restore_stack then
         taps = [pkg.taps_to_tiled(t) for t in taps]          # takes the tile-major tail
+    taps_fn = lambda k, x: taps
+    if producer:
+        # the four tap branches' last two layers run per target: half-resolution activations (synthetic, fixed) -> tile-major taps
+        del taps
+        acts = [torch.relu(torch.randn((1, K, H // 2, W // 2), device=dev, generator=gen)) for _ in range(4)]
+        prods = [pkg.ModuleTapProducer(tiled=True).to(dev) for _ in range(4)]
+        taps = None
+        taps_fn = lambda k, x: [m(a) for m, a in zip(prods, acts)]
     flow_np, _ = synth.random_fold_flow(H, W, 555)
     flow = torch.from_numpy(np.ascontiguousarray(flow_np.transpose(2, 0, 1))[None]).to(dev).permute(0, 2, 3, 1)
     tile = synth.em_section(min(H, 1024), min(W, 1024), 0)
@@ -839,19 +850,25 @@ def run_c5_stack(pkg, dev, rank, world, dist, sections=100, size=4096, to_host=F
             kw["host_out"] = {n: torch.empty((hi - lo, H, W), dtype=torch.uint8).pin_memory() for n in ("interp", "warped", "stitch")}
         warm = torch.empty((4, H, W), dtype=torch.uint8).pin_memory()
         warm[:] = stack[lo:lo + 4] if hi - lo >= 2 else 0
-        pkg.restore_stack(warm, lambda k, x: taps, lambda k, xk, interp: flow, rank=0, world_size=1, device=dev)   # warm-up
+        pkg.restore_stack(warm, taps_fn, lambda k, xk, interp: flow, rank=0, world_size=1, device=dev)   # warm-up
         if world > 1:
             shard.gather_sections(torch.zeros((1, 8, 8), dtype=torch.uint8, device=dev), world, dst=0)             # communicator
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler = ClockSampler(dev.index or 0) if rank == 0 else None   # sustained FFMA load moves the SM clock: report it per run
+        if sampler is not None:
+            sampler.start()
+            time.sleep(0.15)
+        w0 = time.time()
         t0 = time.perf_counter()
         e0.record()
-        out = pkg.restore_stack(stack, lambda k, x: taps, lambda k, xk, interp: flow, **kw)
+        out = pkg.restore_stack(stack, taps_fn, lambda k, xk, interp: flow, **kw)
         e1.record()
         torch.cuda.synchronize()
         wall_ms = (time.perf_counter() - t0) * 1e3
+        clocks = sampler.stop(w0, time.time()) if sampler is not None else None
     finally:
         pkg.set_gray_replicated("off")
     ms = torch.tensor([max(e0.elapsed_time(e1), wall_ms if to_host else 0.0)], device=dev, dtype=torch.float64)
@@ -862,14 +879,15 @@ def run_c5_stack(pkg, dev, rank, world, dist, sections=100, size=4096, to_host=F
     st = out["stats"]
     res = {"workload": f"{sections} sections {H}x{W}, {len(targets)} targets", "n_gpus": world, "scaling": "strong",
            "seconds": round(sec, 4), "sections_per_s": round(len(targets) / sec, 2), "mpix_per_s": round(len(targets) * H * W / sec / 1e6, 1),
-           "targets_on_busiest_rank": per_rank_max, "ideal_speedup_at_this_n": round(len(targets) / per_rank_max, 3),
+           "clocks_rank0": clocks, "targets_on_busiest_rank": per_rank_max, "ideal_speedup_at_this_n": round(len(targets) / per_rank_max, 3),
            "ms_per_target_on_busiest_rank": round(sec * 1e3 / per_rank_max, 3),
            "h2d_bytes_rank0": st["h2d_bytes"], "d2h_bytes_rank0": st["d2h_bytes"], "kernel_launches_rank0": st["kernel_launches"],
            "outputs": ("interp, warped, stitch: uint8, each rank downloads its own targets into pinned host memory (one async copy per target, no collective)"
                        if to_host else "interp, warped, stitch: uint8 [98,H,W] each, gathered to rank 0 (device memory)"),
-           "taps": "tile-major [1,H/8,W/8,51,8,8] (interpolation_tail_tiled)" if tiled_taps else "[1,51,H,W] (fused interpolation_tail)",
+           "taps": ("produced per target by 4 x ModuleTapProducer (upsample x2 + conv 3x3, tcgen05 TF32) from half-resolution activations, tile-major"
+                    if producer else "tile-major [1,H/8,W/8,51,8,8] (interpolation_tail_tiled)" if tiled_taps else "[1,51,H,W] (fused interpolation_tail)"),
            "api": "sstem_restoration_b200.restore_stack(stack_u8_pinned, taps_fn, flow_fn, rank, world_size, dst=0)"}
-    del taps, flow, stack, out
+    del taps, taps_fn, flow, stack, out
     torch.cuda.empty_cache()
     return res
 
