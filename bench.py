@@ -853,14 +853,14 @@ def run_c5_stack(pkg, dev, rank, world, dist, sections=100, size=4096, to_host=F
         pkg.restore_stack(warm, taps_fn, lambda k, xk, interp: flow, rank=0, world_size=1, device=dev)   # warm-up
         if world > 1:
             shard.gather_sections(torch.zeros((1, 8, 8), dtype=torch.uint8, device=dev), world, dst=0)             # communicator
+        sampler = ClockSampler(dev.index or 0) if rank == 0 else None   # sustained FFMA load moves the SM clock: report it per run
+        if sampler is not None:                                # (started BEFORE the barrier: every rank enters the timed region together)
+            sampler.start()
+            time.sleep(0.15)
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        sampler = ClockSampler(dev.index or 0) if rank == 0 else None   # sustained FFMA load moves the SM clock: report it per run
-        if sampler is not None:
-            sampler.start()
-            time.sleep(0.15)
         w0 = time.time()
         t0 = time.perf_counter()
         e0.record()
