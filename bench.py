@@ -466,6 +466,7 @@ def run_gpu_arm(args):
             c5_host = run_c5_stack(pkg, dev, rank, world, dist if world > 1 else None, args.sections, args.section_size, to_host=True)
         c5_tiled = run_c5_stack(pkg, dev, rank, world, dist if world > 1 else None, args.sections, args.section_size, tiled_taps=True)
         c5_prod = run_c5_stack(pkg, dev, rank, world, dist if world > 1 else None, args.sections, args.section_size, producer=True)
+        torch.cuda.empty_cache()
 
     # ---- warp (configs 4 / 5), the other BASELINE configurations, section-8f rows: rank 0, beside the headline
     warp = run_warp(args, pkg, dev) if not args.no_warp else None
@@ -884,7 +885,8 @@ def run_c5_stack(pkg, dev, rank, world, dist, sections=100, size=4096, to_host=F
                     if producer else "tile-major [1,H/8,W/8,51,8,8] (interpolation_tail_tiled)" if tiled_taps else "[1,51,H,W] (fused interpolation_tail)"),
            "api": "sstem_restoration_b200.restore_stack(stack_u8_pinned, taps_fn, flow_fn, rank, world_size, dst=0)"}
     del taps, taps_fn, flow, stack, out
-    torch.cuda.empty_cache()
+    # (no empty_cache() here: handing the blocks back makes the NEXT config-5 run cudaMalloc gigabytes inside its timed region --
+    #  measured 84 - 161 instead of 148 / 176 sections/s, profiles/c5_order_r2.md; main() frees once after the last variant)
     return res
 
 
