@@ -852,6 +852,13 @@ def run_c5_stack(pkg, dev, rank, world, dist, sections=100, size=4096, to_host=F
         warm = torch.empty((4, H, W), dtype=torch.uint8).pin_memory()
         warm[:] = stack[lo:lo + 4] if hi - lo >= 2 else 0
         pkg.restore_stack(warm, taps_fn, lambda k, xk, interp: flow, rank=0, world_size=1, device=dev)   # warm-up
+        # allocator warm-up: blocks of the sizes the timed call will ask for (its three [targets,H,W] outputs, the gathered copies
+        # on rank 0) are obtained from the driver now and handed to torch's cache -- the timed region measures the job, not
+        # cudaMalloc of gigabytes (which moved config 5 between 84 and 149 sections/s, profiles/c5_order_r2.md)
+        pre = [torch.empty((hi - lo, H, W), dtype=torch.uint8, device=dev) for _ in range(3)]
+        if world > 1 and rank == 0 and not to_host:
+            pre += [torch.empty((len(targets), H, W), dtype=torch.uint8, device=dev) for _ in range(3)]
+        del pre
         if world > 1:
             shard.gather_sections(torch.zeros((1, 8, 8), dtype=torch.uint8, device=dev), world, dst=0)             # communicator
         # (no nvidia-smi sampler here: its start-up attaches to the driver and stalls the ~1000 launches / copies of this job --
