@@ -45,6 +45,9 @@ def tap_conv3x3(x: torch.Tensor, packed_weight: torch.Tensor, bias=None, cin=Non
     if x.dtype != torch.float32 or x.dim() != 4:
         raise TypeError("tap_conv3x3: float32 [B, cin, h, w] required")
     assert x.is_contiguous() == True
+    if torch.is_grad_enabled() and x.requires_grad:
+        # forward only: returning a tensor without a graph would silently cut the gradient of everything upstream
+        raise NotImplementedError("tap_conv3x3 is forward only (the stack-restoration path): call it under torch.no_grad() or detach its input")
     if cin is None or cout is None:
         cin, cout = getattr(packed_weight, "_sstem_cin_cout", (None, None))
         if cin is None:

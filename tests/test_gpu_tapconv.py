@@ -137,3 +137,13 @@ def test_large_image_against_fp32_library_convolution():
     assert abs(float((got - want).mean())) <= 1e-5
     tiled = pkg.tap_conv3x3(x, pkg.pack_tap_conv_weight(w), b, tiled=True)
     assert torch.equal(tiled, pkg.taps_to_tiled(got))
+
+
+def test_forward_only_is_loud_under_autograd():
+    x = torch.rand((1, 51, 8, 8), device="cuda", requires_grad=True)
+    m = pkg.ModuleTapProducer().cuda()
+    with pytest.raises(NotImplementedError):
+        m(x)
+    with torch.no_grad():
+        assert m(x).shape == (1, 51, 16, 16)
+    assert m(x.detach()).requires_grad is False
