@@ -856,8 +856,14 @@ def run_c5_stack(pkg, dev, rank, world, dist, sections=100, size=4096, to_host=F
         # on rank 0) are obtained from the driver now and handed to torch's cache -- the timed region measures the job, not
         # cudaMalloc of gigabytes (which moved config 5 between 84 and 149 sections/s, profiles/c5_order_r2.md)
         pre = [torch.empty((hi - lo, H, W), dtype=torch.uint8, device=dev) for _ in range(3)]
-        if world > 1 and rank == 0 and not to_host:
-            pre += [torch.empty((len(targets), H, W), dtype=torch.uint8, device=dev) for _ in range(3)]
+        if world > 1 and not to_host:
+            m = shard.max_units_per_rank(len(targets), world)
+            if hi - lo < m:                                    # a rank with fewer targets pads its shard for the gather
+                pre.append(torch.empty((m, H, W), dtype=torch.uint8, device=dev))
+            if rank == 0:                                      # receive buffers [world * m, H, W] and, if ragged, the trimmed copies
+                pre += [torch.empty((world * m, H, W), dtype=torch.uint8, device=dev) for _ in range(3)]
+                if world * m != len(targets):
+                    pre += [torch.empty((len(targets), H, W), dtype=torch.uint8, device=dev) for _ in range(3)]
         del pre
         if world > 1:
             shard.gather_sections(torch.zeros((1, 8, 8), dtype=torch.uint8, device=dev), world, dst=0)             # communicator
@@ -876,13 +882,18 @@ def run_c5_stack(pkg, dev, rank, world, dist, sections=100, size=4096, to_host=F
     finally:
         pkg.set_gray_replicated("off")
     ms = torch.tensor([max(e0.elapsed_time(e1), wall_ms if to_host else 0.0)], device=dev, dtype=torch.float64)
+    per_rank_ms = [round(float(ms.item()), 2)]
     if dist is not None:
+        allms = [torch.zeros_like(ms) for _ in range(world)]
+        dist.all_gather(allms, ms)
+        per_rank_ms = [round(float(t.item()), 2) for t in allms]
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     sec = float(ms.item()) * 1e-3
     per_rank_max = -(-len(targets) // world)
     st = out["stats"]
     res = {"workload": f"{sections} sections {H}x{W}, {len(targets)} targets", "n_gpus": world, "scaling": "strong",
            "seconds": round(sec, 4), "sections_per_s": round(len(targets) / sec, 2), "mpix_per_s": round(len(targets) * H * W / sec / 1e6, 1),
+           "per_rank_ms": per_rank_ms,
            "targets_on_busiest_rank": per_rank_max, "ideal_speedup_at_this_n": round(len(targets) / per_rank_max, 3),
            "ms_per_target_on_busiest_rank": round(sec * 1e3 / per_rank_max, 3),
            "h2d_bytes_rank0": st["h2d_bytes"], "d2h_bytes_rank0": st["d2h_bytes"], "kernel_launches_rank0": st["kernel_launches"],
