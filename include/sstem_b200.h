@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SSTEM_ABI_VERSION 2
+#define SSTEM_ABI_VERSION 3
 
 /* argument errors (negative) */
 #define SSTEM_E_NULL      (-1)  /* a required pointer is NULL */

@@ -13,7 +13,7 @@ import threading
 from ._build import LIB_PATH as _DEFAULT_LIB_PATH, needs_build as _needs_build
 
 #: must equal SSTEM_ABI_VERSION of include/sstem_b200.h (checked against the loaded library in load())
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 #: SSTEM_LIB_PATH selects another build of the same library (kernel-tuning experiments)
 LIB_PATH = os.environ.get("SSTEM_LIB_PATH") or _DEFAULT_LIB_PATH
