@@ -272,3 +272,18 @@ def test_tap_producer_restatement_matches_reference_model(golden_dir):
     x, w = r.standard_normal((1, 3, 5, 6)), r.standard_normal((2, 3, 3, 3))
     want = torch.nn.functional.conv2d(torch.from_numpy(x), torch.from_numpy(w), padding=1).numpy()
     assert np.abs(oracle.tap_conv3x3_restated(x, w, None, upsample=False) - want).max() <= 1e-12
+
+
+@pytest.mark.parametrize("h,w", [(1, 1), (1, 7), (2, 2), (3, 5), (9, 4), (16, 16), (13, 31)])
+def test_upsample_restatement_matches_torch_for_odd_sizes(h, w):
+    """nn.Upsample(scale_factor=2, bilinear, align_corners=True) is torch's (model_interp.py:18 only configures it): the
+    restatement's float32 index / weight expressions must reproduce torch CPU for every size, degenerate ones included."""
+    r = np.random.default_rng(h * 100 + w)
+    x = r.standard_normal((2, 3, h, w)).astype(np.float32)
+    want = torch.nn.functional.interpolate(torch.from_numpy(x), scale_factor=2, mode="bilinear", align_corners=True).numpy()
+    got = oracle.upsample2x_align_corners_restated(x, np.float32)
+    assert got.shape == want.shape and np.abs(got - want).max() <= 1e-6
+    w9 = r.standard_normal((4, 3, 3, 3)).astype(np.float32)
+    b = r.standard_normal(4).astype(np.float32)
+    ref = torch.nn.functional.conv2d(torch.from_numpy(want).double(), torch.from_numpy(w9).double(), torch.from_numpy(b).double(), padding=1).numpy()
+    assert np.abs(oracle.tap_conv3x3_restated(x, w9, b) - ref).max() <= 1e-5
